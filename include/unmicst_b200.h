@@ -1,0 +1,167 @@
+/*
+ * unmicst_b200 — C-ABI of the B200-native UnMicst probability-map engine.
+ *
+ * This is the drop-in boundary for the one hot path of HMS-IDAC/UnMicst:
+ *   tile -> UNet2D forward -> ramp-weighted stitch -> uint8 probability maps.
+ * Every entry point names the reference interface it replaces (file:line in the
+ * reference tree).  Plain pointers and sizes only; no C++ or torch types; no
+ * exceptions cross the boundary.  All functions return 0 (UMX_OK) or a negative
+ * UMX_E* code; the message is available from umx_last_error() (thread-local).
+ *
+ * Ownership: the caller owns every pointer it passes (host pageable, host pinned
+ * or device memory — the library asks the driver which).  The library owns all
+ * device memory, streams and events it creates; umx_destroy releases them.
+ * Threading: a handle is bound to one device and must be driven by one thread at
+ * a time; different handles may run concurrently from different threads (ctypes
+ * drops the GIL for the duration of a call).  There is no global mutable state.
+ */
+#ifndef UNMICST_B200_H
+#define UNMICST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UMX_ABI_VERSION 1
+
+/* status codes */
+#define UMX_OK            0
+#define UMX_EINVAL       -1   /* bad argument / unsupported model description   */
+#define UMX_ENOTENSOR    -2   /* a tensor the graph needs is missing / misshaped */
+#define UMX_ECUDA        -3   /* CUDA runtime or driver error                    */
+#define UMX_ENOMEM       -4   /* host or device allocation failed                */
+#define UMX_ENODEVICE    -5   /* no usable sm_100 device                         */
+
+/* graph generations */
+#define UMX_GRAPH_LEGACY  0   /* UnMicst.py:51-187                                */
+#define UMX_GRAPH_V2      1   /* UnMicst1-5.py:55-237, UnMicst2.py, UnMicstCyto2.py */
+
+/* image sample types accepted by umx_infer_image */
+#define UMX_U8   0
+#define UMX_U16  1
+#define UMX_F32  2
+#define UMX_F64  3
+
+/* arithmetic of the wide convolutions (umx_opts.precision / umx_model_desc.precision) */
+#define UMX_PREC_DEFAULT  0   /* library default (currently UMX_PREC_SPLIT3 where the tensor path applies) */
+#define UMX_PREC_FP32     1   /* every layer in fp32 FMA on the CUDA cores (exact reference arithmetic)     */
+#define UMX_PREC_SPLIT3   2   /* tcgen05 fp16 hi/lo split, 3 MMAs per product, fp32 accumulate (~fp32)      */
+#define UMX_PREC_SINGLE   3   /* tcgen05 fp16 operands, 1 MMA per product, fp32 accumulate                  */
+
+typedef struct umx_handle umx_handle;
+
+/* hp.data of a model folder (UnMicst1-5.py:57-67) plus the graph generation. */
+typedef struct umx_model_desc {
+    int32_t abi_version;     /* = UMX_ABI_VERSION */
+    int32_t graph;           /* UMX_GRAPH_*       */
+    int32_t im_size;         /* hp['imSize']   S  */
+    int32_t n_channels;      /* hp['nChannels'] C */
+    int32_t n_classes;       /* hp['nClasses'] K  */
+    int32_t n_out0;          /* hp['nOut0']       */
+    int32_t n_layers;        /* hp['nLayers']     */
+    int32_t feat_maps_fact;  /* hp['featMapsFact']*/
+    int32_t down_samp_fact;  /* hp['downSampFact'] (must be 2) */
+    int32_t ks;              /* hp['ks'] in {1,3,5} */
+    int32_t n_extra_convs;   /* hp['nExtraConvs'] */
+    int32_t precision;       /* UMX_PREC_*        */
+    int32_t max_batch_tiles; /* tiles per forward launch group; 0 = library default */
+    int32_t reserved[3];
+} umx_model_desc;
+
+/* One named fp32 variable of the checkpoint in TensorFlow layout
+ * (conv kernels HWIO, conv-transpose kernels HW[out][in], vectors [C]). */
+typedef struct umx_tensor {
+    const char*  name;
+    const float* data;       /* host pointer, row-major */
+    int32_t      ndim;
+    int64_t      shape[4];
+} umx_tensor;
+
+/* Host-side pre-map applied per sample before (x-mean)/std, in float64, in the
+ * reference's operation order (UnMicst1-5.py:813-821, UnMicst.py:627-631):
+ *   x = sample * in_scale                       (img_as_float: 1/65535, 1/255 or 1)
+ *   if rescale: x = clip(x, imin, imax); x = (x-imin)/(imax-imin) * (omax-omin) + omin   */
+typedef struct umx_premap {
+    double  in_scale;
+    int32_t rescale;
+    int32_t pad_;
+    double  imin, imax, omin, omax;
+} umx_premap;
+
+typedef struct umx_opts {
+    int32_t tile_row0;       /* band of PI2D tile rows [tile_row0, tile_row1) this call owns; */
+    int32_t tile_row1;       /* tile_row1 <= 0 means "to the last tile row"                    */
+    int32_t precision;       /* UMX_PREC_* override for this call (0 = handle default)         */
+    int32_t flags;           /* UMX_F_*                                                        */
+    const umx_premap* premap;/* NULL = samples are already the float image the network sees   */
+    int64_t out_plane_stride;/* elements between class planes of out_u8/out_f32; 0 = H*W       */
+    int32_t out_row_base;    /* image row that out_* row 0 corresponds to (band-local buffers) */
+    int32_t reserved[5];
+} umx_opts;
+
+#define UMX_F_NO_SYNC  1     /* return without waiting for the device (outputs must be device/pinned) */
+
+/* Per-kernel timing gathered with CUDA events on the handle's stream. */
+typedef struct umx_prof_entry {
+    char     name[48];
+    int64_t  launches;
+    double   ms_total;       /* sum of event-timed durations */
+    double   flops;          /* algorithmic FLOPs over those launches   */
+    double   bytes;          /* algorithmic HBM bytes over those launches */
+} umx_prof_entry;
+
+/* Number of CUDA devices visible; 0 when there is none (never an error).
+ * Replaces toolbox/GPUselect.py:4-22 together with umx_device_free_mem. */
+int umx_device_count(void);
+int umx_device_free_mem(int device, int64_t* free_bytes, int64_t* total_bytes);
+
+/* Build the graph and load weights: UNet2D.singleImageInferenceSetup
+ * (UnMicst1-5.py:656-681: setupWithHP + Saver.restore).  Folds batch-norm,
+ * merges the v2 shortcut, repacks for the kernels, allocates workspaces. */
+int umx_create(const umx_model_desc* desc, const umx_tensor* weights, int32_t n_weights,
+               int32_t device, umx_handle** out);
+
+/* UNet2D.singleImageInferenceCleanup (UnMicst1-5.py:684-685). */
+void umx_destroy(umx_handle* h);
+
+/* Session.run(UNet2D.nn, {tfData: tiles, tfTraining: 0}) (UnMicst1-5.py:704):
+ * tiles [n,S,S,C] fp32 NHWC -> probs [n,S,S,K] fp32 softmax.  Any n >= 0. */
+int umx_forward_tiles(umx_handle* h, const float* tiles_nhwc, int32_t n_tiles, float* probs_nhwc,
+                      int32_t precision);
+
+/* UNet2D.singleImageInference for every class at once (UnMicst1-5.py:687-710 with
+ * PI2D.setup/getPatch/createOutput/patchOutput/getValidOutput,
+ * toolbox/PartitionOfImage.py:23-122) plus np.uint8(255*p) (UnMicst1-5.py:848):
+ * img [C][H][W] samples of `dtype` (plane stride in elements; 0 = H*W) ->
+ * out_u8 [K][rows][W] = floor(255*p) and/or out_f32 [K][rows][W] = p, for the
+ * image rows covered by the tile-row band in `opts` (all rows by default). */
+int umx_infer_image(umx_handle* h, const void* img, int32_t dtype, int32_t n_planes, int32_t H, int32_t W,
+                    int64_t plane_stride, double mean, double std_dev,
+                    uint8_t* out_u8, float* out_f32, const umx_opts* opts);
+
+/* Image rows [row0,row1) produced by a tile-row band (host-side helper for sharding). */
+int umx_band_rows(umx_handle* h, int32_t H, int32_t tile_row0, int32_t tile_row1, int32_t* row0, int32_t* row1);
+
+/* Use the caller's CUDA stream (cudaStream_t as an integer) for all compute; 0 = library stream. */
+int umx_set_stream(umx_handle* h, uint64_t cuda_stream);
+
+/* Per-kernel event timing: enable, run, then read back (returns number of entries). */
+int umx_profile_enable(umx_handle* h, int32_t on);
+int umx_profile_read(umx_handle* h, umx_prof_entry* out, int32_t capacity, int32_t reset);
+
+/* Kernels launched by this handle since creation (umx_*: claim for "gpu_launches"). */
+int64_t umx_launch_count(umx_handle* h);
+
+/* Pinned host memory for callers that want full-rate async copies. */
+void* umx_host_alloc(int64_t bytes);
+void  umx_host_free(void* p);
+
+const char* umx_last_error(void);
+const char* umx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNMICST_B200_H */

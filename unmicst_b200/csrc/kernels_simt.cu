@@ -1,0 +1,392 @@
+// fp32 CUDA-core kernels of the UnMicst probability-map path (sm_100a).
+//
+//  conv_simt_kernel   tf.nn.conv2d SAME / tf.nn.conv2d_transpose s2 SAME, NHWC fp32, with the
+//                     channel concat (UnMicst1-5.py:196), shortcut add (:106-114), bias /
+//                     batch-norm affine, ReLU / leaky-ReLU and 2x2 max-pool (:117) fused.
+//                     Exact reference arithmetic (fp32 FMA); used for the narrow / first
+//                     layers and as the UMX_PREC_FP32 path of every layer.
+//  top_softmax_kernel lt 1x1 conv + folded BN + softmax (UnMicst1-5.py:212-237)
+//  gather_tiles       PI2D.getPatch + (patch-mean)/std (PartitionOfImage.py:77-82, UnMicst1-5.py:700)
+//  stitch_kernel      PI2D.patchOutput/getValidOutput as an atomic-free gather
+//                     (PartitionOfImage.py:92-122) + np.uint8(255*p) (UnMicst1-5.py:848)
+#include "umx_kernels.cuh"
+#include "../../include/unmicst_b200.h"
+
+namespace umx {
+
+namespace {
+
+constexpr int CK = 8;        // input channels staged per step
+constexpr int COT = 64;      // output channels per CTA
+constexpr int NTHR = 256;    // 16 pixel groups x 16 channel groups
+constexpr int PIX_PER_CTA = 128;
+
+__device__ __forceinline__ float apply_act(float v, int act, float leaky) {
+    if (act == ACT_RELU) return fmaxf(v, 0.f);
+    if (act == ACT_LEAKY) return v > 0.f ? v : v * leaky;
+    return v;
+}
+
+// Each CTA: 128 output pixels (nt image tiles x ph x pw) x 64 output channels of one phase.
+// Each thread: a 2x4 pixel patch x 4 output channels (32 fp32 accumulators).
+__global__ void __launch_bounds__(NTHR) conv_simt_kernel(const __grid_constant__ ConvParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x;
+    const int cg = tid & 15;
+    const int pg = tid >> 4;
+    const int phase = blockIdx.z;
+    const int co0 = blockIdx.y * COT;
+
+    int n0, y0, x0;
+    if (p.nt > 1) {
+        n0 = blockIdx.x * p.nt; y0 = 0; x0 = 0;
+    } else {
+        const int bx = p.in_w / p.pw, by = p.in_h / p.ph;
+        n0 = blockIdx.x / (bx * by);
+        const int r = blockIdx.x % (bx * by);
+        y0 = (r / bx) * p.ph; x0 = (r % bx) * p.pw;
+    }
+    const int gpt = (p.ph >> 1) * (p.pw >> 2);      // thread groups per image tile
+    const int nt_l = pg / gpt;
+    const int rem = pg % gpt;
+    const int py0 = (rem / (p.pw >> 2)) * 2;
+    const int px0 = (rem % (p.pw >> 2)) * 4;
+
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int t = 0; t < p.nterms; ++t) {
+        const ConvTerm& T = p.term[t];
+        const int ntap = T.ntaps[phase];
+        if (ntap == 0) continue;
+        const int prow = p.ph + T.hy0 + T.hy1;
+        const int pcol = p.pw + T.hx0 + T.hx1;
+        const int npix = p.nt * prow * pcol;
+        float* xs = smem;
+        float* ws = smem + ((npix * CK + 3) & ~3);
+        const int ctot = T.c0 + T.c1;
+        const int nch0 = (T.c0 + CK - 1) / CK;
+        const int nch1 = (T.c1 + CK - 1) / CK;
+        for (int cb = 0; cb < nch0 + nch1; ++cb) {
+            const float* src; int C, cbase, wrow;
+            if (cb < nch0) { src = T.src0; C = T.c0; cbase = cb * CK; wrow = cbase; }
+            else { src = T.src1; C = T.c1; cbase = (cb - nch0) * CK; wrow = T.c0 + cbase; }
+            const int cvalid = min(CK, C - cbase);
+            __syncthreads();
+            // ---- stage the input patch (zero outside the image tile: SAME padding per tile)
+            const bool vec = ((C & 3) == 0);
+            for (int idx = tid; idx < npix * 2; idx += NTHR) {
+                const int pix = idx >> 1, half = idx & 1;
+                const int col = pix % pcol;
+                const int rr = pix / pcol;
+                const int row = rr % prow;
+                const int nl = rr / prow;
+                const int gy = y0 + row - T.hy0, gx = x0 + col - T.hx0, gn = n0 + nl;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (gn < p.n_tiles && gy >= 0 && gy < p.in_h && gx >= 0 && gx < p.in_w) {
+                    const float* g = src + (((int64_t)gn * p.in_h + gy) * p.in_w + gx) * C + cbase + half * 4;
+                    const int rem_c = cvalid - half * 4;
+                    if (vec && rem_c >= 4) {
+                        v = __ldg(reinterpret_cast<const float4*>(g));
+                    } else {
+                        if (rem_c > 0) v.x = __ldg(g);
+                        if (rem_c > 1) v.y = __ldg(g + 1);
+                        if (rem_c > 2) v.z = __ldg(g + 2);
+                        if (rem_c > 3) v.w = __ldg(g + 3);
+                    }
+                }
+                *reinterpret_cast<float4*>(xs + pix * CK + half * 4) = v;
+            }
+            // ---- stage the weights [tap][ci][64 co]
+            const bool wvec = ((p.cout & 3) == 0);
+            for (int idx = tid; idx < ntap * CK * (COT / 4); idx += NTHR) {
+                const int c4 = idx & 15;
+                const int ci = (idx >> 4) & (CK - 1);
+                const int tap = idx >> 7;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int co = co0 + c4 * 4;
+                if (ci < cvalid && co < p.cout) {
+                    const float* g = T.w + ((int64_t)T.wi[phase][tap] * ctot + wrow + ci) * p.cout + co;
+                    if (wvec) {
+                        v = __ldg(reinterpret_cast<const float4*>(g));
+                    } else {
+                        v.x = __ldg(g);
+                        if (co + 1 < p.cout) v.y = __ldg(g + 1);
+                        if (co + 2 < p.cout) v.z = __ldg(g + 2);
+                        if (co + 3 < p.cout) v.w = __ldg(g + 3);
+                    }
+                }
+                *reinterpret_cast<float4*>(ws + (tap * CK + ci) * COT + c4 * 4) = v;
+            }
+            __syncthreads();
+            // ---- accumulate
+            for (int tap = 0; tap < ntap; ++tap) {
+                const int dy = T.dy[phase][tap] + T.hy0;
+                const int dx = T.dx[phase][tap] + T.hx0;
+                const float* xb = xs + ((nt_l * prow + py0 + dy) * pcol + px0 + dx) * CK;
+                const float* wb = ws + tap * CK * COT + cg * 4;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float4 wv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) wv[j] = *reinterpret_cast<const float4*>(wb + (h * 4 + j) * COT);
+#pragma unroll
+                    for (int pp = 0; pp < 8; ++pp) {
+                        const float4 a = *reinterpret_cast<const float4*>(xb + ((pp >> 2) * pcol + (pp & 3)) * CK + h * 4);
+                        acc[pp][0] = fmaf(a.x, wv[0].x, acc[pp][0]); acc[pp][1] = fmaf(a.x, wv[0].y, acc[pp][1]);
+                        acc[pp][2] = fmaf(a.x, wv[0].z, acc[pp][2]); acc[pp][3] = fmaf(a.x, wv[0].w, acc[pp][3]);
+                        acc[pp][0] = fmaf(a.y, wv[1].x, acc[pp][0]); acc[pp][1] = fmaf(a.y, wv[1].y, acc[pp][1]);
+                        acc[pp][2] = fmaf(a.y, wv[1].z, acc[pp][2]); acc[pp][3] = fmaf(a.y, wv[1].w, acc[pp][3]);
+                        acc[pp][0] = fmaf(a.z, wv[2].x, acc[pp][0]); acc[pp][1] = fmaf(a.z, wv[2].y, acc[pp][1]);
+                        acc[pp][2] = fmaf(a.z, wv[2].z, acc[pp][2]); acc[pp][3] = fmaf(a.z, wv[2].w, acc[pp][3]);
+                        acc[pp][0] = fmaf(a.w, wv[3].x, acc[pp][0]); acc[pp][1] = fmaf(a.w, wv[3].y, acc[pp][1]);
+                        acc[pp][2] = fmaf(a.w, wv[3].z, acc[pp][2]); acc[pp][3] = fmaf(a.w, wv[3].w, acc[pp][3]);
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- epilogue: bias -> activation -> post affine -> (pool) -> store
+    const int gn = n0 + nt_l;
+    const int co = co0 + cg * 4;
+    if (gn >= p.n_tiles || co >= p.cout) return;
+    float b[4] = {0.f, 0.f, 0.f, 0.f}, ps[4] = {1.f, 1.f, 1.f, 1.f}, pt[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (co + j < p.cout) {
+            if (p.bias) b[j] = __ldg(p.bias + co + j);
+            if (p.post_scale) { ps[j] = __ldg(p.post_scale + co + j); pt[j] = __ldg(p.post_shift + co + j); }
+        }
+    }
+#pragma unroll
+    for (int pp = 0; pp < 8; ++pp)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v = apply_act(acc[pp][j] + b[j], p.act, p.leaky);
+            if (p.post_scale) v = fmaf(v, ps[j], pt[j]);
+            acc[pp][j] = v;
+        }
+    const bool ovec = ((p.cout & 3) == 0);
+    if (p.pool) {
+        const int oh = p.in_h >> 1, ow = p.in_w >> 1;
+        const int oy = (y0 + py0) >> 1;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int ox = ((x0 + px0) >> 1) + q;
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                v[j] = fmaxf(fmaxf(acc[2 * q][j], acc[2 * q + 1][j]), fmaxf(acc[4 + 2 * q][j], acc[4 + 2 * q + 1][j]));
+            float* o = p.out + (((int64_t)gn * oh + oy) * ow + ox) * p.cout + co;
+            if (ovec) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+            else
+                for (int j = 0; j < 4; ++j) if (co + j < p.cout) o[j] = v[j];
+        }
+    } else {
+        const int oh = p.in_h * p.os, ow = p.in_w * p.os;
+        const int phy = (p.os == 2) ? (phase >> 1) : 0, phx = (p.os == 2) ? (phase & 1) : 0;
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+            const int oy = (y0 + py0 + (pp >> 2)) * p.os + phy;
+            const int ox = (x0 + px0 + (pp & 3)) * p.os + phx;
+            float* o = p.out + (((int64_t)gn * oh + oy) * ow + ox) * p.cout + co;
+            if (ovec) *reinterpret_cast<float4*>(o) = make_float4(acc[pp][0], acc[pp][1], acc[pp][2], acc[pp][3]);
+            else
+                for (int j = 0; j < 4; ++j) if (co + j < p.cout) o[j] = acc[pp][j];
+        }
+    }
+}
+
+// One thread per pixel: K logits from cin channels, then a numerically stable softmax.
+template <int K>
+__global__ void __launch_bounds__(256) top_softmax_kernel(const TopParams p) {
+    extern __shared__ float wsm[];              // [cin][K] + [K]
+    for (int i = threadIdx.x; i < p.cin * K; i += blockDim.x) wsm[i] = p.w[i];
+    if (threadIdx.x < K) wsm[p.cin * K + threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+    __syncthreads();
+    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= p.n_pix) return;
+    const float* x = p.src + pix * p.cin;
+    float z[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) z[k] = 0.f;
+    if ((p.cin & 3) == 0) {
+        for (int c = 0; c < p.cin; c += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(x + c));
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                z[k] = fmaf(v.x, wsm[(c + 0) * K + k], z[k]);
+                z[k] = fmaf(v.y, wsm[(c + 1) * K + k], z[k]);
+                z[k] = fmaf(v.z, wsm[(c + 2) * K + k], z[k]);
+                z[k] = fmaf(v.w, wsm[(c + 3) * K + k], z[k]);
+            }
+        }
+    } else {
+        for (int c = 0; c < p.cin; ++c) {
+            const float v = __ldg(x + c);
+#pragma unroll
+            for (int k = 0; k < K; ++k) z[k] = fmaf(v, wsm[c * K + k], z[k]);
+        }
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { z[k] += wsm[p.cin * K + k]; m = fmaxf(m, z[k]); }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { z[k] = expf(z[k] - m); s += z[k]; }
+    const float inv = 1.f / s;
+#pragma unroll
+    for (int k = 0; k < K; ++k) p.probs[pix * K + k] = z[k] * inv;
+}
+
+__device__ __forceinline__ double load_sample(const void* img, int dtype, int64_t i) {
+    switch (dtype) {
+        case UMX_U8:  return (double)reinterpret_cast<const uint8_t*>(img)[i];
+        case UMX_U16: return (double)reinterpret_cast<const uint16_t*>(img)[i];
+        case UMX_F32: return (double)reinterpret_cast<const float*>(img)[i];
+        default:      return reinterpret_cast<const double*>(img)[i];
+    }
+}
+
+// out[t][y][x][c] = float((frame - mean)/std); frame = premap(sample) inside the image, 0 outside.
+__global__ void __launch_bounds__(256) gather_tiles_kernel(const GatherParams p) {
+    const int64_t total = (int64_t)p.n_tiles * p.S * p.S;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int x = (int)(i % p.S);
+    const int y = (int)((i / p.S) % p.S);
+    const int tl = (int)(i / ((int64_t)p.S * p.S));
+    const int t = p.tile0 + tl;
+    const int ti = t / p.npc, tj = t % p.npc;
+    const int r = ti * p.sub + y - p.margin;     // image row
+    const int c = tj * p.sub + x - p.margin;     // image col
+    const bool inside = (r >= 0 && r < p.H && c >= 0 && c < p.W);
+    for (int ch = 0; ch < p.C; ++ch) {
+        double v = 0.0;
+        if (inside) {
+            const int plane = (p.n_planes == 1) ? 0 : ch;
+            v = load_sample(p.img, p.dtype, (int64_t)plane * p.plane_stride + (int64_t)(r - p.img_row0) * p.W + c);
+            if (p.has_pre) {
+                v = v * p.pre.in_scale;
+                if (p.pre.rescale) {
+                    v = fmin(fmax(v, p.pre.imin), p.pre.imax);
+                    v = (v - p.pre.imin) / (p.pre.imax - p.pre.imin);
+                    v = v * (p.pre.omax - p.pre.omin) + p.pre.omin;
+                }
+            }
+        }
+        p.out[i * p.C + ch] = (float)((v - p.mean) / p.std_dev);
+    }
+}
+
+__device__ __forceinline__ float ramp(int v, int S, int two_m) {
+    const int d = min(v, S - 1 - v);
+    return fminf(1.f, (float)d / (float)two_m);
+}
+
+// One thread per output pixel; every class.  Each pixel is covered by <= 2x2 tiles.
+template <int K>
+__global__ void __launch_bounds__(256) stitch_kernel(const StitchParams p) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = p.row0 + blockIdx.y;
+    if (c >= p.W || r >= p.row1) return;
+    const int R = r + p.margin, Cc = c + p.margin;      // padded-frame coordinates
+    const int two_m = 2 * p.margin;
+    int ti1 = min(R / p.sub, p.npr - 1);
+    int tj1 = min(Cc / p.sub, p.npc - 1);
+    float num[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) num[k] = 0.f;
+    float cnt = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int ti = ti1 - a;
+        if (ti < 0) continue;
+        const int y = R - ti * p.sub;
+        if (y >= p.S) continue;
+        const float wy = ramp(y, p.S, two_m);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int tj = tj1 - b;
+            if (tj < 0) continue;
+            const int x = Cc - tj * p.sub;
+            if (x >= p.S) continue;
+            const float w = fminf(wy, ramp(x, p.S, two_m));
+            cnt += w;
+            if (w > 0.f) {
+                const float* q = p.probs + ((((int64_t)(ti - p.tr_lo) * p.npc + tj) * p.S + y) * p.S + x) * K;
+#pragma unroll
+                for (int k = 0; k < K; ++k) num[k] = fmaf(__ldg(q + k), w, num[k]);
+            }
+        }
+    }
+    const int64_t o = (int64_t)(r - p.out_row_base) * p.W + c;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const float v = num[k] / cnt;
+        if (p.out_f32) p.out_f32[k * p.out_plane_stride + o] = v;
+        if (p.out_u8) p.out_u8[k * p.out_plane_stride + o] = (uint8_t)fminf(255.f, floorf(255.f * v));
+    }
+}
+
+}  // namespace
+
+size_t conv_simt_smem_bytes(const ConvParams& p) {
+    size_t best = 0;
+    for (int t = 0; t < p.nterms; ++t) {
+        const ConvTerm& T = p.term[t];
+        int mt = 0;
+        for (int ph = 0; ph < p.nphase; ++ph) mt = T.ntaps[ph] > mt ? T.ntaps[ph] : mt;
+        const size_t npix = (size_t)p.nt * (p.ph + T.hy0 + T.hy1) * (p.pw + T.hx0 + T.hx1);
+        const size_t fl = ((npix * CK + 3) & ~(size_t)3) + (size_t)mt * CK * COT;
+        best = fl > best ? fl : best;
+    }
+    return best * sizeof(float);
+}
+
+cudaError_t conv_simt_configure() {
+    return cudaFuncSetAttribute(conv_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+}
+
+cudaError_t launch_conv_simt(const ConvParams& p, cudaStream_t s) {
+    dim3 grid;
+    if (p.nt > 1) grid.x = (p.n_tiles + p.nt - 1) / p.nt;
+    else grid.x = (unsigned)((int64_t)p.n_tiles * (p.in_h / p.ph) * (p.in_w / p.pw));
+    grid.y = (p.cout + COT - 1) / COT;
+    grid.z = p.nphase;
+    conv_simt_kernel<<<grid, NTHR, conv_simt_smem_bytes(p), s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_top_softmax(const TopParams& p, cudaStream_t s) {
+    const unsigned blocks = (unsigned)((p.n_pix + 255) / 256);
+    const size_t sm = (size_t)(p.cin * p.k + p.k) * sizeof(float);
+    if (p.k == 2) top_softmax_kernel<2><<<blocks, 256, sm, s>>>(p);
+    else if (p.k == 3) top_softmax_kernel<3><<<blocks, 256, sm, s>>>(p);
+    else if (p.k == 4) top_softmax_kernel<4><<<blocks, 256, sm, s>>>(p);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_tiles(const GatherParams& p, cudaStream_t s) {
+    const int64_t total = (int64_t)p.n_tiles * p.S * p.S;
+    if (total == 0) return cudaSuccess;
+    gather_tiles_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stitch(const StitchParams& p, cudaStream_t s) {
+    if (p.row1 <= p.row0) return cudaSuccess;
+    dim3 grid((p.W + 255) / 256, p.row1 - p.row0);
+    if (p.K == 2) stitch_kernel<2><<<grid, 256, 0, s>>>(p);
+    else if (p.K == 3) stitch_kernel<3><<<grid, 256, 0, s>>>(p);
+    else if (p.K == 4) stitch_kernel<4><<<grid, 256, 0, s>>>(p);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+}  // namespace umx

@@ -1,0 +1,782 @@
+// C-ABI of the engine (include/unmicst_b200.h): model build (fold / repack / plan),
+// tile forward, whole-image tiling driver, profiling.  Host code only; kernels live in
+// kernels_simt.cu (fp32 CUDA cores) and kernels_tc.cu (tcgen05 tensor path).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "umx_internal.h"
+
+namespace umx {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+constexpr float kBnEps = 1e-3f;      // FusedBatchNorm epsilon of every shipped graph
+constexpr float kLeaky = 0.2f;       // LeakyRelu alpha of the v2 graphs
+
+const HostTensor* find(const umx_handle* h, const std::string& name) {
+    auto it = h->tensors.find(name);
+    return it == h->tensors.end() ? nullptr : &it->second;
+}
+
+int need(const umx_handle* h, const std::string& name, std::vector<int64_t> shape, const HostTensor** out) {
+    const HostTensor* t = find(h, name);
+    if (!t) { set_error("tensor '%s' required by the graph is missing", name.c_str()); return UMX_ENOTENSOR; }
+    if (t->shape != shape) {
+        std::string got, want;
+        for (auto d : t->shape) got += std::to_string(d) + ",";
+        for (auto d : shape) want += std::to_string(d) + ",";
+        set_error("tensor '%s' has shape [%s] but the graph needs [%s]", name.c_str(), got.c_str(), want.c_str());
+        return UMX_ENOTENSOR;
+    }
+    *out = t;
+    return UMX_OK;
+}
+
+int upload(umx_handle* h, const std::vector<float>& v, float** out) {
+    float* d = nullptr;
+    UMX_CUDA_TRY(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(float)));
+    h->dev_allocs.push_back(d);
+    if (!v.empty()) UMX_CUDA_TRY(cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    *out = d;
+    return UMX_OK;
+}
+
+int new_buffer(umx_handle* h, const std::string& name, int hh, int ww, int c) {
+    Buffer b; b.name = name; b.h = hh; b.w = ww; b.c = c;
+    h->bufs.push_back(b);
+    return (int)h->bufs.size() - 1;
+}
+
+// gamma/sqrt(var+eps) and beta - mu*scale of one batch-norm scope
+int bn_affine(const umx_handle* h, const std::string& scope, int c, std::vector<float>* scale, std::vector<float>* shift) {
+    const HostTensor *g, *b, *mu, *var;
+    UMX_TRY(need(h, scope + "/gamma", {c}, &g));
+    UMX_TRY(need(h, scope + "/beta", {c}, &b));
+    UMX_TRY(need(h, scope + "/moving_mean", {c}, &mu));
+    UMX_TRY(need(h, scope + "/moving_variance", {c}, &var));
+    scale->resize(c); shift->resize(c);
+    for (int i = 0; i < c; ++i) {
+        const float s = g->data[i] / sqrtf(var->data[i] + kBnEps);
+        (*scale)[i] = s;
+        (*shift)[i] = b->data[i] - mu->data[i] * s;
+    }
+    return UMX_OK;
+}
+
+void conv_taps(ConvTerm* T, int k) {
+    const int r = (k - 1) / 2;
+    T->ntaps[0] = (int8_t)(k * k);
+    for (int a = 0; a < k; ++a)
+        for (int b = 0; b < k; ++b) {
+            const int t = a * k + b;
+            T->dy[0][t] = (int8_t)(a - r); T->dx[0][t] = (int8_t)(b - r); T->wi[0][t] = (int8_t)t;
+        }
+    T->hy0 = T->hy1 = T->hx0 = T->hx1 = r;
+}
+
+// tf.nn.conv2d_transpose stride 2 SAME as four sub-pixel phases:
+// out[2q+p] gathers taps a with (p + pb - a) even from input row q + (p + pb - a)/2.
+void convt_taps(ConvTerm* T, int k) {
+    const int pb = (k - 2) / 2;
+    int hy0 = 0, hy1 = 0;
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+            const int ph = py * 2 + px;
+            int n = 0;
+            for (int a = 0; a < k; ++a) {
+                if ((py + pb - a) & 1) continue;
+                for (int b = 0; b < k; ++b) {
+                    if ((px + pb - b) & 1) continue;
+                    const int dy = (py + pb - a) / 2, dx = (px + pb - b) / 2;   // exact: even numerators
+                    T->dy[ph][n] = (int8_t)dy; T->dx[ph][n] = (int8_t)dx; T->wi[ph][n] = (int8_t)(a * k + b);
+                    hy0 = std::max(hy0, -dy); hy1 = std::max(hy1, dy);
+                    ++n;
+                }
+            }
+            T->ntaps[ph] = (int8_t)n;
+        }
+    T->hy0 = T->hx0 = hy0; T->hy1 = T->hx1 = hy1;
+}
+
+void pick_patch(ConvParams* cp) {
+    cp->pw = std::min(16, cp->in_w);
+    cp->ph = std::min(8, cp->in_h);
+    while (cp->ph * cp->pw > 128) cp->ph >>= 1;
+    cp->nt = 128 / (cp->ph * cp->pw);
+}
+
+struct TermSpec {
+    int src0 = -1, src1 = -1;         // buffer ids
+    std::vector<float> w;             // [tap][c0+c1][cout]
+    int k = 3;
+};
+
+// Append a fused conv op: out = pool?(post(act(sum_terms conv + bias)))
+int add_conv(umx_handle* h, const std::string& name, std::vector<TermSpec>& terms, int cout, bool transpose,
+             const std::vector<float>* bias, int act, const std::vector<float>* post_scale,
+             const std::vector<float>* post_shift, bool pool, int* out_buf) {
+    Op op; op.kind = OP_CONV; op.name = name;
+    ConvParams& cp = op.cp;
+    const Buffer& in0 = h->bufs[terms[0].src0];
+    cp.nterms = (int)terms.size();
+    cp.in_h = in0.h; cp.in_w = in0.w; cp.cout = cout;
+    cp.os = transpose ? 2 : 1; cp.nphase = transpose ? 4 : 1;
+    cp.act = act; cp.leaky = kLeaky; cp.pool = pool ? 1 : 0;
+    pick_patch(&cp);
+    double macs = 0, in_elems = 0, wbytes = 0;
+    for (int t = 0; t < cp.nterms; ++t) {
+        ConvTerm& T = cp.term[t];
+        memset(&T, 0, sizeof(T));
+        const Buffer& a = h->bufs[terms[t].src0];
+        T.c0 = a.c;
+        T.c1 = terms[t].src1 >= 0 ? h->bufs[terms[t].src1].c : 0;
+        if (a.h != cp.in_h || a.w != cp.in_w) { set_error("%s: term grid mismatch", name.c_str()); return UMX_EINVAL; }
+        if (transpose) convt_taps(&T, terms[t].k); else conv_taps(&T, terms[t].k);
+        float* dw = nullptr;
+        UMX_TRY(upload(h, terms[t].w, &dw));
+        T.w = dw;
+        const int kk = terms[t].k * terms[t].k;
+        macs += (double)kk * (T.c0 + T.c1) * cout * in0.h * in0.w;     // conv: per out px; convT: per in px
+        in_elems += (double)(T.c0 + T.c1) * in0.h * in0.w;
+        wbytes += (double)terms[t].w.size() * 4;
+    }
+    float* d = nullptr;
+    if (bias) { UMX_TRY(upload(h, *bias, &d)); cp.bias = d; }
+    if (post_scale) {
+        UMX_TRY(upload(h, *post_scale, &d)); cp.post_scale = d;
+        UMX_TRY(upload(h, *post_shift, &d)); cp.post_shift = d;
+    }
+    const int oh = pool ? in0.h / 2 : in0.h * cp.os, ow = pool ? in0.w / 2 : in0.w * cp.os;
+    op.out_buf = new_buffer(h, name, oh, ow, cout);
+    op.flops_per_tile = 2.0 * macs;
+    op.bytes_per_tile = 4.0 * (in_elems + (double)oh * ow * cout);
+    op.weight_bytes = wbytes;
+    // remember the sources by index; pointers are bound after workspace allocation
+    for (int t = 0; t < cp.nterms; ++t) {
+        cp.term[t].src0 = reinterpret_cast<const float*>((intptr_t)terms[t].src0);
+        cp.term[t].src1 = reinterpret_cast<const float*>((intptr_t)terms[t].src1);
+    }
+    h->ops.push_back(op);
+    *out_buf = op.out_buf;
+    return UMX_OK;
+}
+
+std::vector<float> scaled_kernel(const HostTensor& w, const HostTensor* add, const std::vector<float>* scale) {
+    // HWIO [k][k][cin][cout] is already [tap][cin][cout]
+    std::vector<float> out(w.data);
+    const int64_t cout = w.shape[3];
+    if (add) for (size_t i = 0; i < out.size(); ++i) out[i] += add->data[i];
+    if (scale) for (size_t i = 0; i < out.size(); ++i) out[i] *= (*scale)[i % cout];
+    return out;
+}
+
+std::vector<float> transposed_kernel(const HostTensor& w) {
+    // TF conv2d_transpose filter [a][b][cout][cin] -> [tap][cin][cout]
+    const int64_t k = w.shape[0], co = w.shape[2], ci = w.shape[3];
+    std::vector<float> out(w.data.size());
+    for (int64_t t = 0; t < k * k; ++t)
+        for (int64_t o = 0; o < co; ++o)
+            for (int64_t i = 0; i < ci; ++i) out[(t * ci + i) * co + o] = w.data[(t * co + o) * ci + i];
+    return out;
+}
+
+int build_plan(umx_handle* h) {
+    const int L = h->L, k = h->desc.ks, E = h->desc.n_extra_convs, K = h->K;
+    const std::vector<int>& n = h->chan;
+    const bool v2 = h->desc.graph == UMX_GRAPH_V2;
+    const int act = v2 ? ACT_LEAKY : ACT_RELU;
+    h->in_buf = new_buffer(h, "input", h->S, h->S, h->C);
+    std::vector<int> ds{h->in_buf};
+    char nm[128];
+    for (int i = 0; i < L; ++i) {
+        const int src = ds[i];
+        const HostTensor *w1, *wsc;
+        std::vector<float> scale, shift;
+        if (v2) {
+            snprintf(nm, sizeof nm, "downsampling/ld%d/kernelD%d", i, i);
+            UMX_TRY(need(h, nm, {k, k, n[i], n[i + 1]}, &w1));
+            snprintf(nm, sizeof nm, "ld%d/shortcutWeights", i);
+            UMX_TRY(need(h, nm, {k, k, n[i], n[i + 1]}, &wsc));
+            snprintf(nm, sizeof nm, "ld%d/batch_normalization", i);
+            UMX_TRY(bn_affine(h, nm, n[i + 1], &scale, &shift));
+        } else {
+            snprintf(nm, sizeof nm, "downsampling/ld%d/kernel1", i);
+            UMX_TRY(need(h, nm, {k, k, n[i], n[i + 1]}, &w1));
+            snprintf(nm, sizeof nm, "downsampling/ld%d/shortcutWeights", i);
+            UMX_TRY(need(h, nm, {1, 1, n[i], n[i + 1]}, &wsc));
+            UMX_TRY(bn_affine(h, i == 0 ? std::string("batch_normalization") : "batch_normalization_" + std::to_string(i),
+                              n[i + 1], &scale, &shift));
+        }
+        int cur = src, out = -1;
+        // chain: kernel1/kernelD, then extras; the shortcut joins the LAST conv of the chain
+        for (int e = 0; e <= E; ++e) {
+            const HostTensor* we = w1;
+            if (e > 0) {
+                if (v2) snprintf(nm, sizeof nm, "ld%d/kernelExtra%d", i, e - 1);
+                else snprintf(nm, sizeof nm, "downsampling/ld%d/kernelExtra%d", i, e - 1);
+                UMX_TRY(need(h, nm, {k, k, n[i + 1], n[i + 1]}, &we));
+            }
+            const bool last = (e == E);
+            std::vector<TermSpec> terms(1);
+            terms[0].src0 = cur; terms[0].k = k;
+            snprintf(nm, sizeof nm, "ld%d.conv%d", i, e);
+            if (!last) {
+                terms[0].w = scaled_kernel(*we, nullptr, nullptr);
+                UMX_TRY(add_conv(h, nm, terms, n[i + 1], false, nullptr, act, nullptr, nullptr, false, &out));
+            } else if (v2) {
+                // leaky(BN(c + s)) -> fold BN scale into both linear maps; merge them when they share the input
+                if (E == 0) {
+                    terms[0].w = scaled_kernel(*we, wsc, &scale);
+                } else {
+                    terms[0].w = scaled_kernel(*we, nullptr, &scale);
+                    TermSpec sc; sc.src0 = src; sc.k = k; sc.w = scaled_kernel(*wsc, nullptr, &scale);
+                    terms.push_back(sc);
+                }
+                UMX_TRY(add_conv(h, nm, terms, n[i + 1], false, &shift, act, nullptr, nullptr, true, &out));
+            } else {
+                // BN(relu(c + s)): shortcut is a 1x1 conv of the layer input; BN stays a post-activation affine
+                terms[0].w = scaled_kernel(*we, nullptr, nullptr);
+                TermSpec sc; sc.src0 = src; sc.k = 1; sc.w = scaled_kernel(*wsc, nullptr, nullptr);
+                terms.push_back(sc);
+                UMX_TRY(add_conv(h, nm, terms, n[i + 1], false, nullptr, act, &scale, &shift, true, &out));
+            }
+            cur = out;
+        }
+        ds.push_back(cur);
+    }
+    // bottom
+    int u = -1;
+    {
+        const HostTensor* wb;
+        UMX_TRY(need(h, "lb/kernel1", {k, k, n[L], n[L + 1]}, &wb));
+        std::vector<TermSpec> terms(1);
+        terms[0].src0 = ds[L]; terms[0].k = k;
+        if (v2) {
+            std::vector<float> scale, shift;
+            UMX_TRY(bn_affine(h, "conv", n[L + 1], &scale, &shift));
+            terms[0].w = scaled_kernel(*wb, nullptr, &scale);
+            UMX_TRY(add_conv(h, "lb.conv", terms, n[L + 1], false, &shift, act, nullptr, nullptr, false, &u));
+        } else {
+            terms[0].w = scaled_kernel(*wb, nullptr, nullptr);
+            UMX_TRY(add_conv(h, "lb.conv", terms, n[L + 1], false, nullptr, act, nullptr, nullptr, false, &u));
+        }
+    }
+    // up path
+    for (int i = L - 1; i >= 0; --i) {
+        const HostTensor *wu, *w2;
+        if (v2) snprintf(nm, sizeof nm, "lu%d/kernelU%d", i, i); else snprintf(nm, sizeof nm, "upsampling/lu%d/kernel1", i);
+        UMX_TRY(need(h, nm, {k, k, n[i + 1], n[i + 2]}, &wu));
+        if (v2) snprintf(nm, sizeof nm, "lu%d/kernel2", i); else snprintf(nm, sizeof nm, "upsampling/lu%d/kernel2", i);
+        UMX_TRY(need(h, nm, {k, k, n[i] + n[i + 1], n[i + 1]}, &w2));
+        int us = -1, cv = -1;
+        {
+            std::vector<TermSpec> terms(1);
+            terms[0].src0 = u; terms[0].k = k; terms[0].w = transposed_kernel(*wu);
+            snprintf(nm, sizeof nm, "lu%d.convT", i);
+            UMX_TRY(add_conv(h, nm, terms, n[i + 1], true, nullptr, act, nullptr, nullptr, false, &us));
+        }
+        {
+            std::vector<TermSpec> terms(1);
+            terms[0].src0 = ds[i]; terms[0].src1 = us; terms[0].k = k;
+            snprintf(nm, sizeof nm, "lu%d.conv2", i);
+            if (v2) {
+                std::vector<float> scale, shift;
+                char sc[64]; snprintf(sc, sizeof sc, "lu%d/conv2", i);
+                UMX_TRY(bn_affine(h, sc, n[i + 1], &scale, &shift));
+                terms[0].w = scaled_kernel(*w2, nullptr, &scale);
+                UMX_TRY(add_conv(h, nm, terms, n[i + 1], false, &shift, act, nullptr, nullptr, false, &cv));
+            } else {
+                terms[0].w = scaled_kernel(*w2, nullptr, nullptr);
+                UMX_TRY(add_conv(h, nm, terms, n[i + 1], false, nullptr, act, nullptr, nullptr, false, &cv));
+            }
+        }
+        for (int e = 0; e < E; ++e) {
+            const HostTensor* we;
+            if (v2) snprintf(nm, sizeof nm, "lu%d/kernel2Extra%d", i, e); else snprintf(nm, sizeof nm, "upsampling/lu%d/kernel2Extra%d", i, e);
+            UMX_TRY(need(h, nm, {k, k, n[i + 1], n[i + 1]}, &we));
+            std::vector<TermSpec> terms(1);
+            terms[0].src0 = cv; terms[0].k = k; terms[0].w = scaled_kernel(*we, nullptr, nullptr);
+            snprintf(nm, sizeof nm, "lu%d.extra%d", i, e);
+            UMX_TRY(add_conv(h, nm, terms, n[i + 1], false, nullptr, act, nullptr, nullptr, false, &cv));
+        }
+        u = cv;
+    }
+    // top: 1x1 conv (+ BN on the logits in v2) + softmax
+    {
+        const HostTensor* wt;
+        UMX_TRY(need(h, "lt/kernel", {1, 1, n[1], K}, &wt));
+        Op op; op.kind = OP_TOP; op.name = "lt.softmax";
+        std::vector<float> w(wt->data), bias;
+        if (v2) {
+            std::vector<float> scale, shift;
+            UMX_TRY(bn_affine(h, "batch_normalization", K, &scale, &shift));
+            for (size_t i = 0; i < w.size(); ++i) w[i] *= scale[i % K];
+            bias = shift;
+        }
+        float* d = nullptr;
+        UMX_TRY(upload(h, w, &d)); op.tp.w = d;
+        if (!bias.empty()) { UMX_TRY(upload(h, bias, &d)); op.tp.bias = d; }
+        op.tp.cin = n[1]; op.tp.k = K;
+        op.top_src = u;
+        op.flops_per_tile = 2.0 * n[1] * K * h->S * h->S;
+        op.bytes_per_tile = 4.0 * (double)(n[1] + K) * h->S * h->S;
+        h->ops.push_back(op);
+    }
+    return UMX_OK;
+}
+
+int alloc_workspace(umx_handle* h) {
+    for (auto& b : h->bufs) {
+        UMX_CUDA_TRY(cudaMalloc(&b.d, (size_t)h->max_batch * b.per_tile() * sizeof(float)));
+    }
+    UMX_CUDA_TRY(cudaMalloc(&h->probs, (size_t)h->max_batch * h->S * h->S * h->K * sizeof(float)));
+    for (auto& op : h->ops) {
+        if (op.kind == OP_CONV) {
+            for (int t = 0; t < op.cp.nterms; ++t) {
+                const int s0 = (int)(intptr_t)op.cp.term[t].src0, s1 = (int)(intptr_t)op.cp.term[t].src1;
+                op.cp.term[t].src0 = h->bufs[s0].d;
+                op.cp.term[t].src1 = s1 >= 0 ? h->bufs[s1].d : nullptr;
+            }
+            op.cp.out = h->bufs[op.out_buf].d;
+            if (conv_simt_smem_bytes(op.cp) > 100 * 1024) { set_error("%s: shared-memory tile too large", op.name.c_str()); return UMX_EINVAL; }
+        } else {
+            op.tp.src = h->bufs[op.top_src].d;
+        }
+        ProfSlot ps; ps.name = op.name;
+        op.prof_slot = (int)h->prof.size();
+        h->prof.push_back(ps);
+    }
+    return UMX_OK;
+}
+
+cudaEvent_t grab_event(umx_handle* h) {
+    if (!h->event_pool.empty()) { cudaEvent_t e = h->event_pool.back(); h->event_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct ScopedTimer {
+    umx_handle* h; int slot; double flops, bytes; cudaEvent_t a = nullptr;
+    ScopedTimer(umx_handle* hh, int s, double f, double b) : h(hh), slot(s), flops(f), bytes(b) {
+        if (h->profiling) { a = grab_event(h); cudaEventRecord(a, h->stream); }
+    }
+    ~ScopedTimer() {
+        if (h->profiling) {
+            cudaEvent_t b = grab_event(h);
+            cudaEventRecord(b, h->stream);
+            h->pending.push_back({slot, a, b, flops, bytes});
+        }
+    }
+};
+
+int aux_slot(umx_handle* h, const char* name) {
+    for (size_t i = 0; i < h->prof.size(); ++i) if (h->prof[i].name == name) return (int)i;
+    ProfSlot ps; ps.name = name; h->prof.push_back(ps);
+    return (int)h->prof.size() - 1;
+}
+
+void drain_profile(umx_handle* h) {
+    for (auto& pe : h->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pe.a, pe.b) == cudaSuccess) {
+            ProfSlot& s = h->prof[pe.slot];
+            s.launches += 1; s.ms += ms; s.flops += pe.flops; s.bytes += pe.bytes;
+        }
+        h->event_pool.push_back(pe.a); h->event_pool.push_back(pe.b);
+    }
+    h->pending.clear();
+}
+
+// Run the network on nb tiles already sitting in the input buffer; probs -> `probs_out` (device).
+int run_network(umx_handle* h, int nb, float* probs_out) {
+    for (auto& op : h->ops) {
+        ScopedTimer tm(h, op.prof_slot, op.flops_per_tile * nb, op.bytes_per_tile * nb + op.weight_bytes);
+        if (op.kind == OP_CONV) {
+            ConvParams cp = op.cp;
+            cp.n_tiles = nb;
+            UMX_CUDA_TRY(launch_conv_simt(cp, h->stream));
+        } else {
+            TopParams tp = op.tp;
+            tp.n_pix = (int64_t)nb * h->S * h->S;
+            tp.probs = probs_out;
+            UMX_CUDA_TRY(launch_top_softmax(tp, h->stream));
+        }
+        h->launches += 1;
+    }
+    return UMX_OK;
+}
+
+int ensure(void** p, size_t* cap, size_t bytes) {
+    if (*cap >= bytes && *p) return UMX_OK;
+    if (*p) UMX_CUDA_TRY(cudaFree(*p));
+    *p = nullptr; *cap = 0;
+    UMX_CUDA_TRY(cudaMalloc(p, bytes));
+    *cap = bytes;
+    return UMX_OK;
+}
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+size_t dtype_size(int dtype) {
+    switch (dtype) { case UMX_U8: return 1; case UMX_U16: return 2; case UMX_F32: return 4; case UMX_F64: return 8; }
+    return 0;
+}
+
+}  // namespace
+}  // namespace umx
+
+using namespace umx;
+
+extern "C" {
+
+const char* umx_last_error(void) { return g_err; }
+const char* umx_version(void) { return "unmicst_b200 0.1 (sm_100a)"; }
+
+int umx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int umx_device_free_mem(int device, int64_t* free_bytes, int64_t* total_bytes) {
+    int cur = 0;
+    UMX_CUDA_TRY(cudaGetDevice(&cur));
+    UMX_CUDA_TRY(cudaSetDevice(device));
+    size_t f = 0, t = 0;
+    cudaError_t e = cudaMemGetInfo(&f, &t);
+    cudaSetDevice(cur);
+    UMX_CUDA_TRY(e);
+    if (free_bytes) *free_bytes = (int64_t)f;
+    if (total_bytes) *total_bytes = (int64_t)t;
+    return UMX_OK;
+}
+
+void* umx_host_alloc(int64_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocPortable) != cudaSuccess) {
+        set_error("cudaHostAlloc(%lld) failed", (long long)bytes);
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void umx_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int umx_create(const umx_model_desc* desc, const umx_tensor* weights, int32_t n_weights, int32_t device, umx_handle** out) {
+    if (!desc || !out || (!weights && n_weights > 0)) { set_error("umx_create: null argument"); return UMX_EINVAL; }
+    *out = nullptr;
+    if (desc->abi_version != UMX_ABI_VERSION) { set_error("umx_create: ABI version %d != %d", desc->abi_version, UMX_ABI_VERSION); return UMX_EINVAL; }
+    if (desc->graph != UMX_GRAPH_LEGACY && desc->graph != UMX_GRAPH_V2) { set_error("unknown graph %d", desc->graph); return UMX_EINVAL; }
+    if (desc->down_samp_fact != 2) { set_error("downSampFact %d unsupported (only 2)", desc->down_samp_fact); return UMX_EINVAL; }
+    if (desc->ks != 1 && desc->ks != 3 && desc->ks != 5) { set_error("ks %d unsupported (1, 3 or 5)", desc->ks); return UMX_EINVAL; }
+    if (desc->n_classes < 2 || desc->n_classes > 4) { set_error("nClasses %d unsupported (2..4)", desc->n_classes); return UMX_EINVAL; }
+    if (desc->n_channels < 1 || desc->n_out0 < 1 || desc->n_layers < 1 || desc->feat_maps_fact < 1 || desc->n_extra_convs < 0) {
+        set_error("invalid hyper-parameters"); return UMX_EINVAL;
+    }
+    const int S = desc->im_size;
+    if (S < 8 || (S & (S - 1)) || (S >> desc->n_layers) < 4) {
+        set_error("imSize %d with %d layers unsupported (power of two, deepest grid >= 4)", S, desc->n_layers);
+        return UMX_EINVAL;
+    }
+    int ndev = umx_device_count();
+    if (ndev <= 0) { set_error("no CUDA device visible (this engine has no CPU path)"); return UMX_ENODEVICE; }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (have %d)", device, ndev); return UMX_EINVAL; }
+    cudaDeviceProp prop;
+    UMX_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { set_error("device %d is sm_%d%d; this build targets sm_100a (B200) only", device, prop.major, prop.minor); return UMX_ENODEVICE; }
+    UMX_CUDA_TRY(cudaSetDevice(device));
+
+    umx_handle* h = new (std::nothrow) umx_handle();
+    if (!h) { set_error("out of host memory"); return UMX_ENOMEM; }
+    h->device = device; h->desc = *desc;
+    h->S = S; h->C = desc->n_channels; h->K = desc->n_classes; h->L = desc->n_layers;
+    h->margin = S / 8; h->sub = S - 2 * h->margin;
+    h->chan = {desc->n_channels, desc->n_out0};
+    for (int i = 0; i < desc->n_layers; ++i) h->chan.push_back(h->chan.back() * desc->feat_maps_fact);
+    for (int i = 0; i < n_weights; ++i) {
+        const umx_tensor& t = weights[i];
+        if (!t.name || !t.data || t.ndim < 1 || t.ndim > 4) { set_error("weights[%d] malformed", i); umx_destroy(h); return UMX_EINVAL; }
+        HostTensor ht;
+        for (int d = 0; d < t.ndim; ++d) ht.shape.push_back(t.shape[d]);
+        ht.data.assign(t.data, t.data + ht.numel());
+        h->tensors[t.name] = std::move(ht);
+    }
+    int rc = build_plan(h);
+    if (rc != UMX_OK) { umx_destroy(h); return rc; }
+    // batch: enough tiles to fill 148 SMs several times over, bounded by workspace memory
+    int64_t per_tile = 0;
+    for (auto& b : h->bufs) per_tile += b.per_tile() * 4;
+    per_tile += (int64_t)S * S * h->K * 4;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    int64_t mb = desc->max_batch_tiles > 0 ? desc->max_batch_tiles : std::max<int64_t>(64, (int64_t)(16.0 * 1024 * 1024 * 1024 / per_tile));
+    mb = std::min<int64_t>(mb, std::max<int64_t>(1, (int64_t)(free_b * 0.5 / per_tile)));
+    mb = std::min<int64_t>(mb, 4096);
+    h->max_batch = (int)mb;
+    rc = alloc_workspace(h);
+    if (rc != UMX_OK) { umx_destroy(h); return rc; }
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("stream creation failed"); umx_destroy(h); return UMX_ECUDA;
+    }
+    h->stream = h->own_stream;
+    for (int i = 0; i < 2; ++i) {
+        cudaEventCreateWithFlags(&h->ev_stitch[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming);
+    }
+    if (conv_simt_configure() != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError())); umx_destroy(h); return UMX_ECUDA; }
+    h->tensors.clear();   // host copies no longer needed
+    *out = h;
+    return UMX_OK;
+}
+
+void umx_destroy(umx_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    drain_profile(h);
+    for (auto e : h->event_pool) cudaEventDestroy(e);
+    for (auto p : h->dev_allocs) cudaFree(p);
+    for (auto& b : h->bufs) if (b.d) cudaFree(b.d);
+    if (h->probs) cudaFree(h->probs);
+    if (h->d_img) cudaFree(h->d_img);
+    if (h->d_probs_rows) cudaFree(h->d_probs_rows);
+    for (int i = 0; i < 2; ++i) {
+        if (h->d_stage_u8[i]) cudaFree(h->d_stage_u8[i]);
+        if (h->d_stage_f32[i]) cudaFree(h->d_stage_f32[i]);
+        if (h->ev_stitch[i]) cudaEventDestroy(h->ev_stitch[i]);
+        if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
+    }
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    delete h;
+}
+
+int umx_set_stream(umx_handle* h, uint64_t cuda_stream) {
+    if (!h) { set_error("null handle"); return UMX_EINVAL; }
+    h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    return UMX_OK;
+}
+
+int umx_profile_enable(umx_handle* h, int32_t on) {
+    if (!h) { set_error("null handle"); return UMX_EINVAL; }
+    h->profiling = on != 0;
+    return UMX_OK;
+}
+
+int umx_profile_read(umx_handle* h, umx_prof_entry* out, int32_t capacity, int32_t reset) {
+    if (!h) { set_error("null handle"); return UMX_EINVAL; }
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    drain_profile(h);
+    int n = 0;
+    for (auto& s : h->prof) {
+        if (out && n < capacity) {
+            memset(&out[n], 0, sizeof(out[n]));
+            strncpy(out[n].name, s.name.c_str(), sizeof(out[n].name) - 1);
+            out[n].launches = s.launches; out[n].ms_total = s.ms; out[n].flops = s.flops; out[n].bytes = s.bytes;
+        }
+        ++n;
+        if (reset) { s.launches = 0; s.ms = 0; s.flops = 0; s.bytes = 0; }
+    }
+    return n;
+}
+
+int64_t umx_launch_count(umx_handle* h) { return h ? h->launches : 0; }
+
+int umx_forward_tiles(umx_handle* h, const float* tiles, int32_t n_tiles, float* probs, int32_t precision) {
+    (void)precision;
+    if (!h || n_tiles < 0 || (n_tiles > 0 && (!tiles || !probs))) { set_error("umx_forward_tiles: bad argument"); return UMX_EINVAL; }
+    UMX_CUDA_TRY(cudaSetDevice(h->device));
+    const size_t in_tile = (size_t)h->S * h->S * h->C, out_tile = (size_t)h->S * h->S * h->K;
+    for (int t0 = 0; t0 < n_tiles; t0 += h->max_batch) {
+        const int nb = std::min(h->max_batch, n_tiles - t0);
+        UMX_CUDA_TRY(cudaMemcpyAsync(h->bufs[h->in_buf].d, tiles + (size_t)t0 * in_tile, nb * in_tile * sizeof(float),
+                                     cudaMemcpyDefault, h->stream));
+        UMX_TRY(run_network(h, nb, h->probs));
+        UMX_CUDA_TRY(cudaMemcpyAsync(probs + (size_t)t0 * out_tile, h->probs, nb * out_tile * sizeof(float),
+                                     cudaMemcpyDefault, h->stream));
+        // the host buffers may be pageable: finish this group before the input buffer is reused
+        UMX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    drain_profile(h);
+    return UMX_OK;
+}
+
+int umx_band_rows(umx_handle* h, int32_t H, int32_t tr0, int32_t tr1, int32_t* row0, int32_t* row1) {
+    if (!h || H <= 0) { set_error("umx_band_rows: bad argument"); return UMX_EINVAL; }
+    const int npr = (H + h->sub - 1) / h->sub;
+    if (tr1 <= 0 || tr1 > npr) tr1 = npr;
+    if (tr0 < 0 || tr0 >= tr1) { set_error("umx_band_rows: empty band"); return UMX_EINVAL; }
+    const int frame_rows = npr * h->sub + 2 * h->margin;
+    const int p0 = tr0 * h->sub, p1 = (tr1 == npr) ? frame_rows : tr1 * h->sub;
+    if (row0) *row0 = std::min(H, std::max(0, p0 - h->margin));
+    if (row1) *row1 = std::min(H, std::max(0, p1 - h->margin));
+    return UMX_OK;
+}
+
+int umx_infer_image(umx_handle* h, const void* img, int32_t dtype, int32_t n_planes, int32_t H, int32_t W,
+                    int64_t plane_stride, double mean, double std_dev, uint8_t* out_u8, float* out_f32,
+                    const umx_opts* opts) {
+    if (!h || !img || H <= 0 || W <= 0 || dtype_size(dtype) == 0) { set_error("umx_infer_image: bad argument"); return UMX_EINVAL; }
+    if (n_planes != 1 && n_planes != h->C) { set_error("image has %d planes, network takes %d channels", n_planes, h->C); return UMX_EINVAL; }
+    if (!out_u8 && !out_f32) { set_error("umx_infer_image: no output requested"); return UMX_EINVAL; }
+    if (std_dev == 0.0) { set_error("std is zero"); return UMX_EINVAL; }
+    UMX_CUDA_TRY(cudaSetDevice(h->device));
+    const int S = h->S, m = h->margin, sub = h->sub, K = h->K;
+    const int npr = (H + sub - 1) / sub, npc = (W + sub - 1) / sub;
+    const int frame_rows = npr * sub + 2 * m;
+    int ta = opts ? opts->tile_row0 : 0, tb = opts ? opts->tile_row1 : 0;
+    if (tb <= 0 || tb > npr) tb = npr;
+    if (ta < 0 || ta >= tb) { set_error("empty tile-row band [%d,%d) of %d", ta, tb, npr); return UMX_EINVAL; }
+    if (plane_stride == 0) plane_stride = (int64_t)H * W;
+    int64_t out_ps = (opts && opts->out_plane_stride) ? opts->out_plane_stride : (int64_t)H * W;
+    const int out_row_base = opts ? opts->out_row_base : 0;
+    const int t_first = std::max(ta - 1, 0);
+    const size_t esz = dtype_size(dtype);
+
+    // ---- image rows this band touches
+    const int ir0 = std::max(0, t_first * sub - m), ir1 = std::min(H, (tb - 1) * sub + S - m);
+    GatherParams gp{};
+    gp.dtype = dtype; gp.n_planes = n_planes; gp.H = H; gp.W = W; gp.S = S; gp.margin = m; gp.sub = sub; gp.npc = npc;
+    gp.C = h->C; gp.mean = mean; gp.std_dev = std_dev;
+    if (opts && opts->premap) {
+        gp.has_pre = 1;
+        gp.pre.in_scale = opts->premap->in_scale; gp.pre.rescale = opts->premap->rescale;
+        gp.pre.imin = opts->premap->imin; gp.pre.imax = opts->premap->imax;
+        gp.pre.omin = opts->premap->omin; gp.pre.omax = opts->premap->omax;
+    }
+    if (is_device_ptr(img)) {
+        gp.img = img; gp.plane_stride = plane_stride; gp.img_row0 = 0; gp.img_rows = H;
+    } else {
+        const int nrows = ir1 - ir0;
+        void* p = h->d_img;
+        UMX_TRY(ensure(&p, &h->d_img_bytes, (size_t)n_planes * nrows * W * esz));
+        h->d_img = p;
+        for (int pl = 0; pl < n_planes; ++pl) {
+            const char* src = (const char*)img + ((size_t)pl * plane_stride + (size_t)ir0 * W) * esz;
+            char* dst = (char*)h->d_img + (size_t)pl * nrows * W * esz;
+            UMX_CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)nrows * W * esz, cudaMemcpyHostToDevice, h->stream));
+        }
+        gp.img = h->d_img; gp.plane_stride = (int64_t)nrows * W; gp.img_row0 = ir0; gp.img_rows = nrows;
+    }
+
+    // ---- tile-row groups; probs of a group (+ the carried previous tile row) stay on the device
+    const int rpg = std::max(1, h->max_batch / npc);
+    const size_t row_elems = (size_t)npc * S * S * K;
+    {
+        void* p = h->d_probs_rows;
+        UMX_TRY(ensure(&p, &h->d_probs_rows_bytes, (size_t)(rpg + 1) * row_elems * sizeof(float)));
+        h->d_probs_rows = (float*)p;
+    }
+    const bool u8_direct = out_u8 && is_device_ptr(out_u8);
+    const bool f32_direct = out_f32 && is_device_ptr(out_f32);
+    const int max_rows = rpg * sub + 2 * m;
+    if (out_u8 && !u8_direct && h->d_stage_u8_bytes < (size_t)K * max_rows * W) {
+        for (int i = 0; i < 2; ++i) { if (h->d_stage_u8[i]) cudaFree(h->d_stage_u8[i]); h->d_stage_u8[i] = nullptr; }
+        for (int i = 0; i < 2; ++i) UMX_CUDA_TRY(cudaMalloc(&h->d_stage_u8[i], (size_t)K * max_rows * W));
+        h->d_stage_u8_bytes = (size_t)K * max_rows * W;
+    }
+    if (out_f32 && !f32_direct && h->d_stage_f32_bytes < (size_t)K * max_rows * W * 4) {
+        for (int i = 0; i < 2; ++i) { if (h->d_stage_f32[i]) cudaFree(h->d_stage_f32[i]); h->d_stage_f32[i] = nullptr; }
+        for (int i = 0; i < 2; ++i) UMX_CUDA_TRY(cudaMalloc(&h->d_stage_f32[i], (size_t)K * max_rows * W * 4));
+        h->d_stage_f32_bytes = (size_t)K * max_rows * W * 4;
+    }
+    const int s_gather = aux_slot(h, "gather_tiles"), s_stitch = aux_slot(h, "stitch_quantize");
+    int gi = 0;
+    bool copies_pending[2] = {false, false};
+    for (int g0 = t_first; g0 < tb; g0 += rpg, ++gi) {
+        const int g1 = std::min(g0 + rpg, tb);
+        const int lo = (g0 > t_first) ? g0 - 1 : g0;            // first tile row held in d_probs_rows
+        float* group_base = h->d_probs_rows + (size_t)(g0 - lo) * row_elems;
+        const int tile_begin = g0 * npc, tile_end = g1 * npc;
+        for (int t0 = tile_begin; t0 < tile_end; t0 += h->max_batch) {
+            const int nb = std::min(h->max_batch, tile_end - t0);
+            gp.tile0 = t0; gp.n_tiles = nb; gp.out = h->bufs[h->in_buf].d;
+            {
+                ScopedTimer tm(h, s_gather, 0, (double)nb * S * S * (h->C * 4.0 + esz));
+                UMX_CUDA_TRY(launch_gather_tiles(gp, h->stream));
+                h->launches += 1;
+            }
+            UMX_TRY(run_network(h, nb, group_base + (size_t)(t0 - tile_begin) * S * S * K));
+        }
+        // ---- emit the padded-frame rows this group completes
+        const int p0 = std::max(g0, ta) * sub, p1 = (g1 == npr) ? frame_rows : g1 * sub;
+        const int r0 = std::min(H, std::max(0, p0 - m)), r1 = std::min(H, std::max(0, p1 - m));
+        if (r1 > r0) {
+            const int sb = gi & 1;
+            if (copies_pending[sb]) { UMX_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_copy[sb], 0)); copies_pending[sb] = false; }
+            StitchParams sp{};
+            sp.probs = h->d_probs_rows; sp.tr_lo = lo; sp.tr_hi = g1;
+            sp.S = S; sp.margin = m; sp.sub = sub; sp.npc = npc; sp.npr = npr; sp.K = K; sp.H = H; sp.W = W;
+            sp.row0 = r0; sp.row1 = r1;
+            if (out_u8 && out_f32 && u8_direct != f32_direct) {
+                set_error("out_u8 and out_f32 must both be host or both be device pointers"); return UMX_EINVAL;
+            }
+            const bool staged = out_u8 ? !u8_direct : !f32_direct;
+            if (staged) {
+                sp.out_u8 = out_u8 ? h->d_stage_u8[sb] : nullptr;
+                sp.out_f32 = out_f32 ? h->d_stage_f32[sb] : nullptr;
+                sp.out_plane_stride = (int64_t)max_rows * W; sp.out_row_base = r0;
+            } else {
+                sp.out_u8 = out_u8; sp.out_f32 = out_f32; sp.out_plane_stride = out_ps; sp.out_row_base = out_row_base;
+            }
+            {
+                ScopedTimer tm(h, s_stitch, 0, (double)(r1 - r0) * W * K * (4.0 * 1.78 + (out_u8 ? 1 : 0) + (out_f32 ? 4 : 0)));
+                UMX_CUDA_TRY(launch_stitch(sp, h->stream));
+                h->launches += 1;
+            }
+            if (staged) {
+                UMX_CUDA_TRY(cudaEventRecord(h->ev_stitch[sb], h->stream));
+                UMX_CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_stitch[sb], 0));
+                const size_t n = (size_t)(r1 - r0) * W;
+                for (int k = 0; k < K; ++k) {
+                    if (out_u8)
+                        UMX_CUDA_TRY(cudaMemcpyAsync(out_u8 + (size_t)k * out_ps + (size_t)(r0 - out_row_base) * W,
+                                                     h->d_stage_u8[sb] + (size_t)k * max_rows * W, n, cudaMemcpyDeviceToHost, h->copy_stream));
+                    if (out_f32)
+                        UMX_CUDA_TRY(cudaMemcpyAsync(out_f32 + (size_t)k * out_ps + (size_t)(r0 - out_row_base) * W,
+                                                     h->d_stage_f32[sb] + (size_t)k * max_rows * W, n * 4, cudaMemcpyDeviceToHost, h->copy_stream));
+                }
+                UMX_CUDA_TRY(cudaEventRecord(h->ev_copy[sb], h->copy_stream));
+                copies_pending[sb] = true;
+            }
+        }
+        // ---- carry the last tile row of this group into slot 0 for the next group
+        if (g1 < tb) {
+            const float* last = h->d_probs_rows + (size_t)(g1 - 1 - lo) * row_elems;
+            if (last != h->d_probs_rows)
+                UMX_CUDA_TRY(cudaMemcpyAsync(h->d_probs_rows, last, row_elems * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+        }
+    }
+    // make the caller's stream wait for outstanding D2H copies, then (by default) the host too
+    for (int sb = 0; sb < 2; ++sb)
+        if (copies_pending[sb]) UMX_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_copy[sb], 0));
+    if (!(opts && (opts->flags & UMX_F_NO_SYNC))) {
+        UMX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        drain_profile(h);
+    }
+    return UMX_OK;
+}
+
+}  // extern "C"
