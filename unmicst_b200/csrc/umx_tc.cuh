@@ -1,0 +1,57 @@
+// Parameter block of the tcgen05 implicit-GEMM convolution (kernels_tc.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace umx {
+
+struct TcTap { int8_t dy, dx, wi, pad; };
+
+struct TcConvParams {
+    int32_t n_tiles;             // image tiles in this launch
+    int32_t in_h, in_w;          // input grid per image tile
+    int32_t bw, bh, bn;          // TMA box over (w, h, tile): bn*bh*bw = 128 GEMM rows
+    int32_t c0, c1;              // channels of the two concat sources (c1 = 0: single source)
+    int32_t cout;
+    int32_t n_t;                 // GEMM N per CTA tile (multiple of 16, <= 256)
+    int32_t n_ntiles;            // ceil(cout / n_t)
+    int32_t nphase, os;          // conv: 1,1   conv-transpose: 4,2
+    int32_t ntaps[4];
+    TcTap   taps[4][9];
+    int32_t planes;              // 1: fp16 operands, 1 MMA/product; 2: hi/lo split, 3 MMAs/product
+    int32_t stages;              // smem pipeline depth
+    int32_t act;                 // umx::Act
+    float   leaky;
+    int32_t pool;                // fused 2x2 max-pool (conv only)
+    const float* bias;           // [cout] or nullptr
+    __half* out_h;               // fp16 plane(s) [planes][n][oh][ow][cout] or nullptr
+    int64_t out_plane_elems;     // elements between the hi and lo plane
+    int32_t out_planes;          // planes to write into out_h (1 or 2)
+    float*  out_f;               // fp32 [n][oh][ow][cout] or nullptr
+    // narrow skip source handled in fp32 in the epilogue (raw input channels of lu0.conv2)
+    const float* skip_src;       // [n][in_h][in_w][skip_c] or nullptr
+    const float* skip_w;         // [9][skip_c][cout] fp32 (BN scale folded)
+    int32_t skip_c;
+    // fused lt 1x1 conv + softmax (replaces the activation store when top_w != nullptr)
+    const float* top_w;          // [cout][K]
+    const float* top_b;          // [K] or nullptr
+    float* top_probs;            // [n][oh][ow][K]
+    int32_t top_k;
+};
+
+size_t tc_conv_smem_bytes(const TcConvParams& p);
+cudaError_t tc_conv_configure();
+cudaError_t launch_tc_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                           const TcConvParams& p, int num_sms, cudaStream_t s);
+
+// Host helpers: build TMA descriptors through the driver entry point (no libcuda link dependency).
+// activations: fp16 [planes][n][h][w][c]; box = {64 ch, bw, bh, bn, planes}
+int make_act_tensor_map(CUtensorMap* out, const __half* base, int planes, int64_t plane_elems, int n, int h, int w, int c,
+                        int bw, int bh, int bn, int box_planes);
+// weights: fp16 [planes][tap][cout][cin]; box = {64 cin, n_t, 1, planes}
+int make_weight_tensor_map(CUtensorMap* out, const __half* base, int planes, int taps, int cout, int cin, int n_t,
+                           int box_planes);
+
+}  // namespace umx
