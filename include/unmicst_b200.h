@@ -151,6 +151,11 @@ int umx_set_stream(umx_handle* h, uint64_t cuda_stream);
 int umx_profile_enable(umx_handle* h, int32_t on);
 int umx_profile_read(umx_handle* h, umx_prof_entry* out, int32_t capacity, int32_t reset);
 
+/* Debug/bring-up: copy the activation buffer written by op `name` ("ld1.conv0", "lu3.convT", ...)
+ * during the last forward, first n_tiles tiles, to host fp32 NHWC (hi+lo planes are summed).
+ * Returns the element count per tile, or a negative UMX_E* code. */
+int64_t umx_debug_buffer(umx_handle* h, const char* name, int32_t n_tiles, float* out, int64_t capacity);
+
 /* Kernels launched by this handle since creation (umx_*: claim for "gpu_launches"). */
 int64_t umx_launch_count(umx_handle* h);
 

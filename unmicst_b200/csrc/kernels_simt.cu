@@ -27,6 +27,15 @@ __device__ __forceinline__ float apply_act(float v, int act, float leaky) {
     return v;
 }
 
+// 4 consecutive channels -> fp16 hi (and lo = fp16(v - hi)) planes
+__device__ __forceinline__ void store_h2x4(__half* o, int64_t plane_elems, int planes, const float* v) {
+    __half h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { h[j] = __float2half_rn(v[j]); l[j] = __float2half_rn(v[j] - __half2float(h[j])); }
+    *reinterpret_cast<uint2*>(o) = *reinterpret_cast<uint2*>(h);
+    if (planes == 2) *reinterpret_cast<uint2*>(o + plane_elems) = *reinterpret_cast<uint2*>(l);
+}
+
 // Each CTA: 128 output pixels (nt image tiles x ph x pw) x 64 output channels of one phase.
 // Each thread: a 2x4 pixel patch x 4 output channels (32 fp32 accumulators).
 __global__ void __launch_bounds__(NTHR) conv_simt_kernel(const __grid_constant__ ConvParams p) {
@@ -181,10 +190,14 @@ __global__ void __launch_bounds__(NTHR) conv_simt_kernel(const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 v[j] = fmaxf(fmaxf(acc[2 * q][j], acc[2 * q + 1][j]), fmaxf(acc[4 + 2 * q][j], acc[4 + 2 * q + 1][j]));
-            float* o = p.out + (((int64_t)gn * oh + oy) * ow + ox) * p.cout + co;
-            if (ovec) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-            else
-                for (int j = 0; j < 4; ++j) if (co + j < p.cout) o[j] = v[j];
+            const int64_t oo = (((int64_t)gn * oh + oy) * ow + ox) * p.cout + co;
+            if (p.out) {
+                float* o = p.out + oo;
+                if (ovec) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                else
+                    for (int j = 0; j < 4; ++j) if (co + j < p.cout) o[j] = v[j];
+            }
+            if (p.out_h) store_h2x4(p.out_h + oo, p.out_plane_elems, p.out_planes, v);
         }
     } else {
         const int oh = p.in_h * p.os, ow = p.in_w * p.os;
@@ -193,10 +206,14 @@ __global__ void __launch_bounds__(NTHR) conv_simt_kernel(const __grid_constant__
         for (int pp = 0; pp < 8; ++pp) {
             const int oy = (y0 + py0 + (pp >> 2)) * p.os + phy;
             const int ox = (x0 + px0 + (pp & 3)) * p.os + phx;
-            float* o = p.out + (((int64_t)gn * oh + oy) * ow + ox) * p.cout + co;
-            if (ovec) *reinterpret_cast<float4*>(o) = make_float4(acc[pp][0], acc[pp][1], acc[pp][2], acc[pp][3]);
-            else
-                for (int j = 0; j < 4; ++j) if (co + j < p.cout) o[j] = acc[pp][j];
+            const int64_t oo = (((int64_t)gn * oh + oy) * ow + ox) * p.cout + co;
+            if (p.out) {
+                float* o = p.out + oo;
+                if (ovec) *reinterpret_cast<float4*>(o) = make_float4(acc[pp][0], acc[pp][1], acc[pp][2], acc[pp][3]);
+                else
+                    for (int j = 0; j < 4; ++j) if (co + j < p.cout) o[j] = acc[pp][j];
+            }
+            if (p.out_h) store_h2x4(p.out_h + oo, p.out_plane_elems, p.out_planes, acc[pp]);
         }
     }
 }

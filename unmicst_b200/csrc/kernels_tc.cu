@@ -1,0 +1,371 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a.
+//
+// Computes tf.nn.conv2d (3x3, SAME, stride 1) and tf.nn.conv2d_transpose (3x3, stride 2, SAME, as
+// four sub-pixel phases) over NHWC activations of many independent PI2D tiles at once:
+//     GEMM M = 128 output pixels (a TMA box of bn tiles x bh rows x bw cols),
+//          N = n_t output channels (<= 256), K = taps x input channels in 64-channel slabs.
+// A (activations) is fetched per filter tap by a 5-D TMA tiled load whose box origin is shifted by
+// the tap offset; rows/cols outside an image tile are zero-filled by the TMA unit, which is exactly
+// TensorFlow's per-tile SAME padding.  The channel concat [skip, up] of the up path
+// (UnMicst1-5.py:196) is never materialised: the K loop walks two tensor maps.  B (weights, BN
+// folded) is K-major [tap][cout][cin].  Both land in 128B-swizzled shared memory and feed
+// tcgen05.mma (kind::f16, fp32 accumulate in TMEM).  Operands are fp16; in split mode every
+// activation/weight is carried as hi + lo fp16 planes and each product issues three MMAs
+// (hi*hi + hi*lo + lo*hi), which restores ~fp32 accuracy.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocator), warps 2..5 = epilogue
+// (TMEM -> registers -> bias / leaky-ReLU / 2x2 max-pool -> fp16 hi/lo planes or fp32).  Persistent
+// CTAs, two TMEM accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <stdio.h>
+
+#include "umx_kernels.cuh"
+#include "umx_tc.cuh"
+
+namespace umx {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kAPlaneBytes = 128 * 128;       // 128 rows x 64 fp16
+constexpr int kAccStride = 256;               // TMEM columns between the two accumulator stages
+constexpr uint32_t kSpinLimit = 1u << 28;     // trap instead of hanging the GPU on a pipeline bug
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > kSpinLimit) { printf("umx tc_conv: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row swizzle atoms 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TileCoord { int phase, n0, y0, x0, n_idx; };
+
+__device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int tile, int m_tiles) {
+    TileCoord t;
+    t.n_idx = tile % p.n_ntiles;
+    const int mt = (tile / p.n_ntiles) % m_tiles;
+    t.phase = tile / (p.n_ntiles * m_tiles);
+    if (p.bn > 1) { t.n0 = mt * p.bn; t.y0 = 0; t.x0 = 0; }
+    else {
+        const int bx = p.in_w / p.bw, by = p.in_h / p.bh;
+        t.n0 = mt / (bx * by);
+        const int r = mt % (bx * by);
+        t.y0 = (r / bx) * p.bh; t.x0 = (r % bx) * p.bw;
+    }
+    return t;
+}
+
+__device__ __forceinline__ float act_fn(float v, int act, float leaky) {
+    if (act == ACT_RELU) return fmaxf(v, 0.f);
+    if (act == ACT_LEAKY) return v > 0.f ? v : v * leaky;
+    return v;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+               const __grid_constant__ CUtensorMap mapB, const __grid_constant__ TcConvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int a_bytes = p.planes * kAPlaneBytes;
+    const int b_plane_bytes = p.n_t * 128;
+    const int b_bytes = p.planes * b_plane_bytes;
+    const int stage_bytes = a_bytes + b_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    const uint32_t full0 = smem_u32(bars);
+    const uint32_t empty0 = full0 + 8 * p.stages;
+    const uint32_t tfull0 = empty0 + 8 * p.stages;
+    const uint32_t tempty0 = tfull0 + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA0);
+        if (p.c1 > 0) tma_prefetch_desc(&mapA1);
+        tma_prefetch_desc(&mapB);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < p.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+            for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int m_tiles = (p.bn > 1) ? (p.n_tiles + p.bn - 1) / p.bn : p.n_tiles * (p.in_w / p.bw) * (p.in_h / p.bh);
+    const int total = p.nphase * m_tiles * p.n_ntiles;
+    const int nch0 = (p.c0 + 63) >> 6, nch1 = (p.c1 + 63) >> 6;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================= TMA producer =================
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const TileCoord t = decode_tile(p, tile, m_tiles);
+                const int ntap = p.ntaps[t.phase];
+                for (int tp = 0; tp < ntap; ++tp) {
+                    const TcTap tap = p.taps[t.phase][tp];
+                    for (int cb = 0; cb < nch0 + nch1; ++cb) {
+                        const bool second = cb >= nch0;
+                        const int cc = (second ? cb - nch0 : cb) * 64;
+                        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                        const uint32_t fb = full0 + 8 * stage;
+                        mbar_expect_tx(fb, (uint32_t)stage_bytes);
+                        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                        tma_load_5d(sa, second ? &mapA1 : &mapA0, fb, cc, t.x0 + tap.dx, t.y0 + tap.dy, t.n0, 0);
+                        tma_load_4d(sa + a_bytes, &mapB, fb, (second ? p.c0 : 0) + cc, t.n_idx * p.n_t, tap.wi, 0);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ================= MMA issuer =================
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_t >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const TileCoord t = decode_tile(p, tile, m_tiles);
+                const int ntap = p.ntaps[t.phase];
+                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccStride);
+                uint32_t accumulate = 0;
+                for (int tp = 0; tp < ntap; ++tp) {
+                    for (int cb = 0; cb < nch0 + nch1; ++cb) {
+                        const bool second = cb >= nch0;
+                        const int cc = (second ? cb - nch0 : cb) * 64;
+                        const int kvalid = min(64, (second ? p.c1 : p.c0) - cc);
+                        const int nk = (kvalid + 15) >> 4;
+                        mbar_wait(full0 + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                        const uint32_t sb = sa + a_bytes;
+                        for (int k = 0; k < nk; ++k) {
+                            const uint64_t ah = umma_desc(sa + k * 32), bh = umma_desc(sb + k * 32);
+                            umma_f16(tmem_d, ah, bh, idesc, accumulate);
+                            accumulate = 1;
+                            if (p.planes == 2) {
+                                const uint64_t al = umma_desc(sa + kAPlaneBytes + k * 32);
+                                const uint64_t bl = umma_desc(sb + b_plane_bytes + k * 32);
+                                umma_f16(tmem_d, ah, bl, idesc, 1);
+                                umma_f16(tmem_d, al, bh, idesc, 1);
+                            }
+                        }
+                        umma_commit(empty0 + 8 * stage);          // frees the smem slot when these MMAs retire
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+                umma_commit(tfull0 + 8 * acc);                    // accumulator ready for the epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ================= epilogue (4 warps, one TMEM lane quarter each) =================
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int xl = m % p.bw, yl = (m / p.bw) % p.bh, nl = m / (p.bw * p.bh);
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            const TileCoord t = decode_tile(p, tile, m_tiles);
+            const int n = t.n0 + nl, y = t.y0 + yl, x = t.x0 + xl;
+            const bool valid = n < p.n_tiles;
+            int oh, ow, oy, ox; bool writer = valid;
+            if (p.pool) { oh = p.in_h >> 1; ow = p.in_w >> 1; oy = y >> 1; ox = x >> 1; writer = valid && !(y & 1) && !(x & 1); }
+            else if (p.os == 2) { oh = p.in_h * 2; ow = p.in_w * 2; oy = 2 * y + (t.phase >> 1); ox = 2 * x + (t.phase & 1); }
+            else { oh = p.in_h; ow = p.in_w; oy = y; ox = x; }
+            const int64_t opix = ((int64_t)n * oh + oy) * ow + ox;
+            mbar_wait(tfull0 + 8 * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
+            for (int c16 = 0; c16 < (p.n_t >> 4); ++c16) {
+                uint32_t r[16];
+                tmem_ld16(tbase + c16 * 16, r);
+                const int co = t.n_idx * p.n_t + c16 * 16;
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float b = 0.f;
+                    if (p.bias && co + j < p.cout) b = __ldg(p.bias + co + j);
+                    v[j] = act_fn(__uint_as_float(r[j]) + b, p.act, p.leaky);
+                }
+                if (p.pool) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+                        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], p.bw));
+                    }
+                }
+#pragma unroll
+                for (int h8 = 0; h8 < 2; ++h8) {
+                    const int c = co + h8 * 8;
+                    if (!writer || c >= p.cout) continue;
+                    if (p.out_f) {
+                        float4* o = reinterpret_cast<float4*>(p.out_f + opix * p.cout + c);
+                        o[0] = make_float4(v[h8 * 8 + 0], v[h8 * 8 + 1], v[h8 * 8 + 2], v[h8 * 8 + 3]);
+                        o[1] = make_float4(v[h8 * 8 + 4], v[h8 * 8 + 5], v[h8 * 8 + 6], v[h8 * 8 + 7]);
+                    }
+                    if (p.out_h) {
+                        __half2 hi[4], lo[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float a = v[h8 * 8 + 2 * j], b = v[h8 * 8 + 2 * j + 1];
+                            const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+                            hi[j] = __halves2half2(ha, hb);
+                            lo[j] = __halves2half2(__float2half_rn(a - __half2float(ha)), __float2half_rn(b - __half2float(hb)));
+                        }
+                        __half* o = p.out_h + opix * p.cout + c;
+                        *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(hi);
+                        if (p.out_planes == 2) *reinterpret_cast<uint4*>(o + p.out_plane_elems) = *reinterpret_cast<uint4*>(lo);
+                    }
+                }
+                __syncwarp();        // reconverge before the next .sync.aligned TMEM load
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+}  // namespace
+
+size_t tc_conv_smem_bytes(const TcConvParams& p) {
+    const size_t stage = (size_t)p.planes * (kAPlaneBytes + (size_t)p.n_t * 128);
+    return (size_t)p.stages * stage + (2 * p.stages + 4) * 8 + 16 + 1024;
+}
+
+cudaError_t tc_conv_configure() {
+    return cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+cudaError_t launch_tc_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcConvParams& p,
+                           int num_sms, cudaStream_t s) {
+    const int m_tiles = (p.bn > 1) ? (p.n_tiles + p.bn - 1) / p.bn : p.n_tiles * (p.in_w / p.bw) * (p.in_h / p.bh);
+    const int total = p.nphase * m_tiles * p.n_ntiles;
+    if (total == 0) return cudaSuccess;
+    const int grid = total < num_sms ? total : num_sms;
+    // at least ~120 KB so that exactly one CTA (and its 512 TMEM columns) lives on an SM
+    size_t smem = tc_conv_smem_bytes(p);
+    if (smem < 120 * 1024) smem = 120 * 1024;
+    tc_conv_kernel<<<grid, kThreads, smem, s>>>(a0, a1, b, p);
+    return cudaGetLastError();
+}
+
+int make_act_tensor_map(CUtensorMap* out, const __half* base, int planes, int64_t plane_elems, int n, int h, int w, int c,
+                        int bw, int bh, int bn, int box_planes) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return -1;
+    cuuint64_t dims[5] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n, (cuuint64_t)planes};
+    cuuint64_t strides[4] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2, (cuuint64_t)plane_elems * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn, (cuuint32_t)box_planes};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+int make_weight_tensor_map(CUtensorMap* out, const __half* base, int planes, int taps, int cout, int cin, int n_t,
+                           int box_planes) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return -1;
+    cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)taps, (cuuint64_t)planes};
+    cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)cout * cin * 2, (cuuint64_t)taps * cout * cin * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)n_t, 1, (cuuint32_t)box_planes};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+}  // namespace umx

@@ -118,59 +118,36 @@ void pick_patch(ConvParams* cp) {
     cp->nt = 128 / (cp->ph * cp->pw);
 }
 
-struct TermSpec {
-    int src0 = -1, src1 = -1;         // buffer ids
-    std::vector<float> w;             // [tap][c0+c1][cout]
-    int k = 3;
-};
+using TermSpec = TermHost;
 
-// Append a fused conv op: out = pool?(post(act(sum_terms conv + bias)))
+// Append a fused conv op (host-side description only; lowered to a kernel by lower_plan):
+//   out = pool?(post(act(sum_terms conv + bias)))
 int add_conv(umx_handle* h, const std::string& name, std::vector<TermSpec>& terms, int cout, bool transpose,
              const std::vector<float>* bias, int act, const std::vector<float>* post_scale,
              const std::vector<float>* post_shift, bool pool, int* out_buf) {
     Op op; op.kind = OP_CONV; op.name = name;
-    ConvParams& cp = op.cp;
-    const Buffer& in0 = h->bufs[terms[0].src0];
-    cp.nterms = (int)terms.size();
-    cp.in_h = in0.h; cp.in_w = in0.w; cp.cout = cout;
-    cp.os = transpose ? 2 : 1; cp.nphase = transpose ? 4 : 1;
-    cp.act = act; cp.leaky = kLeaky; cp.pool = pool ? 1 : 0;
-    pick_patch(&cp);
+    ConvSpec& sp = op.spec;
+    sp.terms = terms; sp.cout = cout; sp.transpose = transpose; sp.act = act; sp.pool = pool;
+    if (bias) { sp.has_bias = true; sp.bias = *bias; }
+    if (post_scale) { sp.has_post = true; sp.post_scale = *post_scale; sp.post_shift = *post_shift; }
+    const Buffer in0 = h->bufs[terms[0].src0];
     double macs = 0, in_elems = 0, wbytes = 0;
-    for (int t = 0; t < cp.nterms; ++t) {
-        ConvTerm& T = cp.term[t];
-        memset(&T, 0, sizeof(T));
-        const Buffer& a = h->bufs[terms[t].src0];
-        T.c0 = a.c;
-        T.c1 = terms[t].src1 >= 0 ? h->bufs[terms[t].src1].c : 0;
-        if (a.h != cp.in_h || a.w != cp.in_w) { set_error("%s: term grid mismatch", name.c_str()); return UMX_EINVAL; }
-        if (transpose) convt_taps(&T, terms[t].k); else conv_taps(&T, terms[t].k);
-        float* dw = nullptr;
-        UMX_TRY(upload(h, terms[t].w, &dw));
-        T.w = dw;
-        const int kk = terms[t].k * terms[t].k;
-        macs += (double)kk * (T.c0 + T.c1) * cout * in0.h * in0.w;     // conv: per out px; convT: per in px
-        in_elems += (double)(T.c0 + T.c1) * in0.h * in0.w;
-        wbytes += (double)terms[t].w.size() * 4;
+    for (auto& t : terms) {
+        const Buffer& a = h->bufs[t.src0];
+        if (a.h != in0.h || a.w != in0.w) { set_error("%s: term grid mismatch", name.c_str()); return UMX_EINVAL; }
+        const int cin = a.c + (t.src1 >= 0 ? h->bufs[t.src1].c : 0);
+        macs += (double)t.k * t.k * cin * cout * in0.h * in0.w;      // conv: per out px; convT: per in px
+        in_elems += (double)cin * in0.h * in0.w;
+        wbytes += (double)t.w.size() * 4;
     }
-    float* d = nullptr;
-    if (bias) { UMX_TRY(upload(h, *bias, &d)); cp.bias = d; }
-    if (post_scale) {
-        UMX_TRY(upload(h, *post_scale, &d)); cp.post_scale = d;
-        UMX_TRY(upload(h, *post_shift, &d)); cp.post_shift = d;
-    }
-    const int oh = pool ? in0.h / 2 : in0.h * cp.os, ow = pool ? in0.w / 2 : in0.w * cp.os;
+    const int os = transpose ? 2 : 1;
+    const int oh = pool ? in0.h / 2 : in0.h * os, ow = pool ? in0.w / 2 : in0.w * os;
     op.out_buf = new_buffer(h, name, oh, ow, cout);
     op.flops_per_tile = 2.0 * macs;
     op.bytes_per_tile = 4.0 * (in_elems + (double)oh * ow * cout);
     op.weight_bytes = wbytes;
-    // remember the sources by index; pointers are bound after workspace allocation
-    for (int t = 0; t < cp.nterms; ++t) {
-        cp.term[t].src0 = reinterpret_cast<const float*>((intptr_t)terms[t].src0);
-        cp.term[t].src1 = reinterpret_cast<const float*>((intptr_t)terms[t].src1);
-    }
-    h->ops.push_back(op);
-    *out_buf = op.out_buf;
+    h->ops.push_back(std::move(op));
+    *out_buf = h->ops.back().out_buf;
     return UMX_OK;
 }
 
@@ -326,9 +303,7 @@ int build_plan(umx_handle* h) {
             for (size_t i = 0; i < w.size(); ++i) w[i] *= scale[i % K];
             bias = shift;
         }
-        float* d = nullptr;
-        UMX_TRY(upload(h, w, &d)); op.tp.w = d;
-        if (!bias.empty()) { UMX_TRY(upload(h, bias, &d)); op.tp.bias = d; }
+        op.top_w = w; op.top_b = bias;
         op.tp.cin = n[1]; op.tp.k = K;
         op.top_src = u;
         op.flops_per_tile = 2.0 * n[1] * K * h->S * h->S;
@@ -338,21 +313,157 @@ int build_plan(umx_handle* h) {
     return UMX_OK;
 }
 
-int alloc_workspace(umx_handle* h) {
-    for (auto& b : h->bufs) {
-        UMX_CUDA_TRY(cudaMalloc(&b.d, (size_t)h->max_batch * b.per_tile() * sizeof(float)));
+bool tc_eligible(const umx_handle* h, const Op& op) {
+    if (h->precision == UMX_PREC_FP32 || op.kind != OP_CONV) return false;
+    const ConvSpec& sp = op.spec;
+    if (sp.terms.size() != 1 || sp.has_post || sp.terms[0].k != 3) return false;
+    const Buffer& a = h->bufs[sp.terms[0].src0];
+    if (a.c % 8 != 0 || sp.cout % 8 != 0 || a.h < 4 || a.w < 4) return false;
+    if (sp.terms[0].src1 >= 0 && h->bufs[sp.terms[0].src1].c % 8 != 0) return false;
+    return true;
+}
+
+int pick_n_tile(int cout) {
+    const int c16 = (cout + 15) & ~15;
+    for (int n = 256; n >= 16; n -= 16)
+        if (c16 % n == 0) return n;
+    return 16;
+}
+
+// fp32 [tap][cin][cout] -> fp16 [plane][tap][cout][cin] (hi, lo = fp16(w - hi))
+void split_weights(const std::vector<float>& w, int taps, int cin, int cout, int planes, std::vector<__half>* out) {
+    out->assign((size_t)planes * taps * cout * cin, __float2half(0.f));
+    const size_t plane = (size_t)taps * cout * cin;
+    for (int t = 0; t < taps; ++t)
+        for (int i = 0; i < cin; ++i)
+            for (int o = 0; o < cout; ++o) {
+                const float v = w[((size_t)t * cin + i) * cout + o];
+                const __half hi = __float2half_rn(v);
+                const size_t idx = ((size_t)t * cout + o) * cin + i;
+                (*out)[idx] = hi;
+                if (planes == 2) (*out)[plane + idx] = __float2half_rn(v - __half2float(hi));
+            }
+}
+
+int lower_conv_simt(umx_handle* h, Op& op) {
+    const ConvSpec& sp = op.spec;
+    ConvParams& cp = op.cp;
+    memset(&cp, 0, sizeof(cp));
+    const Buffer& in0 = h->bufs[sp.terms[0].src0];
+    cp.nterms = (int)sp.terms.size();
+    cp.in_h = in0.h; cp.in_w = in0.w; cp.cout = sp.cout;
+    cp.os = sp.transpose ? 2 : 1; cp.nphase = sp.transpose ? 4 : 1;
+    cp.act = sp.act; cp.leaky = kLeaky; cp.pool = sp.pool ? 1 : 0;
+    pick_patch(&cp);
+    for (int t = 0; t < cp.nterms; ++t) {
+        ConvTerm& T = cp.term[t];
+        const Buffer& a = h->bufs[sp.terms[t].src0];
+        T.c0 = a.c; T.src0 = a.d;
+        if (sp.terms[t].src1 >= 0) { T.c1 = h->bufs[sp.terms[t].src1].c; T.src1 = h->bufs[sp.terms[t].src1].d; }
+        if (!T.src0 || (sp.terms[t].src1 >= 0 && !T.src1)) { set_error("%s: fp32 source buffer missing", op.name.c_str()); return UMX_EINVAL; }
+        if (sp.transpose) convt_taps(&T, sp.terms[t].k); else conv_taps(&T, sp.terms[t].k);
+        float* dw = nullptr;
+        UMX_TRY(upload(h, sp.terms[t].w, &dw));
+        T.w = dw;
     }
-    UMX_CUDA_TRY(cudaMalloc(&h->probs, (size_t)h->max_batch * h->S * h->S * h->K * sizeof(float)));
+    float* d = nullptr;
+    if (sp.has_bias) { UMX_TRY(upload(h, sp.bias, &d)); cp.bias = d; }
+    if (sp.has_post) {
+        UMX_TRY(upload(h, sp.post_scale, &d)); cp.post_scale = d;
+        UMX_TRY(upload(h, sp.post_shift, &d)); cp.post_shift = d;
+    }
+    const Buffer& ob = h->bufs[op.out_buf];
+    cp.out = ob.d; cp.out_h = ob.dh; cp.out_planes = ob.planes; cp.out_plane_elems = ob.plane_elems;
+    if (cp.out_h && (sp.cout & 3)) { set_error("%s: fp16 output needs cout %% 4 == 0", op.name.c_str()); return UMX_EINVAL; }
+    if (conv_simt_smem_bytes(cp) > 100 * 1024) { set_error("%s: shared-memory tile too large", op.name.c_str()); return UMX_EINVAL; }
+    return UMX_OK;
+}
+
+int lower_conv_tc(umx_handle* h, Op& op) {
+    const ConvSpec& sp = op.spec;
+    TcConvParams& tp = op.tcp;
+    memset(&tp, 0, sizeof(tp));
+    const TermHost& T = sp.terms[0];
+    const Buffer& a0 = h->bufs[T.src0];
+    const Buffer* a1 = T.src1 >= 0 ? &h->bufs[T.src1] : nullptr;
+    const int planes = h->precision == UMX_PREC_SINGLE ? 1 : 2;
+    tp.in_h = a0.h; tp.in_w = a0.w;
+    tp.bw = std::min(a0.w, 16); tp.bh = std::min(a0.h, 128 / tp.bw); tp.bn = 128 / (tp.bw * tp.bh);
+    tp.c0 = a0.c; tp.c1 = a1 ? a1->c : 0;
+    tp.cout = sp.cout; tp.n_t = pick_n_tile(sp.cout); tp.n_ntiles = (sp.cout + tp.n_t - 1) / tp.n_t;
+    tp.nphase = sp.transpose ? 4 : 1; tp.os = sp.transpose ? 2 : 1;
+    ConvTerm tt; memset(&tt, 0, sizeof(tt));
+    if (sp.transpose) convt_taps(&tt, 3); else conv_taps(&tt, 3);
+    for (int ph = 0; ph < tp.nphase; ++ph) {
+        tp.ntaps[ph] = tt.ntaps[ph];
+        for (int i = 0; i < tt.ntaps[ph]; ++i) tp.taps[ph][i] = TcTap{tt.dy[ph][i], tt.dx[ph][i], tt.wi[ph][i], 0};
+    }
+    tp.planes = planes;
+    const size_t stage = (size_t)planes * (16384 + (size_t)tp.n_t * 128);
+    tp.stages = (int)std::min<size_t>(6, (227 * 1024 - 2048) / stage);
+    if (tp.stages < 2) { set_error("%s: pipeline does not fit shared memory", op.name.c_str()); return UMX_EINVAL; }
+    tp.act = sp.act; tp.leaky = kLeaky; tp.pool = sp.pool ? 1 : 0;
+    float* d = nullptr;
+    if (sp.has_bias) { UMX_TRY(upload(h, sp.bias, &d)); tp.bias = d; }
+    const Buffer& ob = h->bufs[op.out_buf];
+    tp.out_f = ob.d; tp.out_h = ob.dh; tp.out_planes = ob.planes; tp.out_plane_elems = ob.plane_elems;
+    // weights -> fp16 planes on the device
+    const int cin = tp.c0 + tp.c1;
+    std::vector<__half> wh;
+    split_weights(T.w, 9, cin, sp.cout, planes, &wh);
+    __half* dw = nullptr;
+    UMX_CUDA_TRY(cudaMalloc(&dw, wh.size() * sizeof(__half)));
+    h->dev_allocs.push_back(reinterpret_cast<float*>(dw));
+    UMX_CUDA_TRY(cudaMemcpy(dw, wh.data(), wh.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    int rc = make_weight_tensor_map(&op.mapB, dw, planes, 9, sp.cout, cin, tp.n_t, planes);
+    if (rc) { set_error("%s: cuTensorMapEncodeTiled(weights) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
+    if (!a0.dh || (a1 && !a1->dh)) { set_error("%s: fp16 source buffer missing", op.name.c_str()); return UMX_EINVAL; }
+    rc = make_act_tensor_map(&op.mapA0, a0.dh, a0.planes, a0.plane_elems, h->cap_tiles, a0.h, a0.w, a0.c, tp.bw, tp.bh, tp.bn, planes);
+    if (rc) { set_error("%s: cuTensorMapEncodeTiled(A0) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
+    if (a1) {
+        rc = make_act_tensor_map(&op.mapA1, a1->dh, a1->planes, a1->plane_elems, h->cap_tiles, a1->h, a1->w, a1->c, tp.bw, tp.bh, tp.bn, planes);
+        if (rc) { set_error("%s: cuTensorMapEncodeTiled(A1) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
+    } else {
+        op.mapA1 = op.mapA0;
+    }
+    return UMX_OK;
+}
+
+// Decide per op which kernel runs it, which formats every buffer must exist in, allocate the
+// workspace and bind device pointers / tensor maps.
+int lower_plan(umx_handle* h) {
+    for (auto& op : h->ops) {
+        op.use_tc = tc_eligible(h, op);
+        if (op.kind == OP_CONV) {
+            for (auto& t : op.spec.terms) {
+                for (int s : {t.src0, t.src1}) {
+                    if (s < 0) continue;
+                    if (op.use_tc) h->bufs[s].need_h = true; else h->bufs[s].need_f = true;
+                }
+            }
+        } else {
+            h->bufs[op.top_src].need_f = true;
+        }
+    }
+    h->bufs[h->in_buf].need_f = true;
+    const int planes = h->precision == UMX_PREC_SINGLE ? 1 : 2;
+    for (auto& b : h->bufs) {
+        if (b.need_f) UMX_CUDA_TRY(cudaMalloc(&b.d, (size_t)h->cap_tiles * b.per_tile() * sizeof(float)));
+        if (b.need_h) {
+            b.planes = planes; b.plane_elems = (int64_t)h->cap_tiles * b.per_tile();
+            UMX_CUDA_TRY(cudaMalloc(&b.dh, (size_t)planes * b.plane_elems * sizeof(__half)));
+            UMX_CUDA_TRY(cudaMemset(b.dh, 0, (size_t)planes * b.plane_elems * sizeof(__half)));
+        }
+    }
+    UMX_CUDA_TRY(cudaMalloc(&h->probs, (size_t)h->cap_tiles * h->S * h->S * h->K * sizeof(float)));
     for (auto& op : h->ops) {
         if (op.kind == OP_CONV) {
-            for (int t = 0; t < op.cp.nterms; ++t) {
-                const int s0 = (int)(intptr_t)op.cp.term[t].src0, s1 = (int)(intptr_t)op.cp.term[t].src1;
-                op.cp.term[t].src0 = h->bufs[s0].d;
-                op.cp.term[t].src1 = s1 >= 0 ? h->bufs[s1].d : nullptr;
-            }
-            op.cp.out = h->bufs[op.out_buf].d;
-            if (conv_simt_smem_bytes(op.cp) > 100 * 1024) { set_error("%s: shared-memory tile too large", op.name.c_str()); return UMX_EINVAL; }
+            if (op.use_tc) UMX_TRY(lower_conv_tc(h, op)); else UMX_TRY(lower_conv_simt(h, op));
+            op.spec = ConvSpec();       // host copies of the weights are no longer needed
         } else {
+            float* d = nullptr;
+            UMX_TRY(upload(h, op.top_w, &d)); op.tp.w = d;
+            if (!op.top_b.empty()) { UMX_TRY(upload(h, op.top_b, &d)); op.tp.bias = d; }
             op.tp.src = h->bufs[op.top_src].d;
         }
         ProfSlot ps; ps.name = op.name;
@@ -405,7 +516,11 @@ void drain_profile(umx_handle* h) {
 int run_network(umx_handle* h, int nb, float* probs_out) {
     for (auto& op : h->ops) {
         ScopedTimer tm(h, op.prof_slot, op.flops_per_tile * nb, op.bytes_per_tile * nb + op.weight_bytes);
-        if (op.kind == OP_CONV) {
+        if (op.kind == OP_CONV && op.use_tc) {
+            TcConvParams tp = op.tcp;
+            tp.n_tiles = nb;
+            UMX_CUDA_TRY(launch_tc_conv(op.mapA0, op.mapA1, op.mapB, tp, h->num_sms, h->stream));
+        } else if (op.kind == OP_CONV) {
             ConvParams cp = op.cp;
             cp.n_tiles = nb;
             UMX_CUDA_TRY(launch_conv_simt(cp, h->stream));
@@ -523,6 +638,9 @@ int umx_create(const umx_model_desc* desc, const umx_tensor* weights, int32_t n_
     int rc = build_plan(h);
     if (rc != UMX_OK) { umx_destroy(h); return rc; }
     // batch: enough tiles to fill 148 SMs several times over, bounded by workspace memory
+    h->num_sms = prop.multiProcessorCount;
+    h->precision = desc->precision == UMX_PREC_DEFAULT ? UMX_PREC_SPLIT3 : desc->precision;
+    if (h->precision < UMX_PREC_FP32 || h->precision > UMX_PREC_SINGLE) { set_error("unknown precision %d", desc->precision); umx_destroy(h); return UMX_EINVAL; }
     int64_t per_tile = 0;
     for (auto& b : h->bufs) per_tile += b.per_tile() * 4;
     per_tile += (int64_t)S * S * h->K * 4;
@@ -532,7 +650,8 @@ int umx_create(const umx_model_desc* desc, const umx_tensor* weights, int32_t n_
     mb = std::min<int64_t>(mb, std::max<int64_t>(1, (int64_t)(free_b * 0.5 / per_tile)));
     mb = std::min<int64_t>(mb, 4096);
     h->max_batch = (int)mb;
-    rc = alloc_workspace(h);
+    h->cap_tiles = (h->max_batch + 7) & ~7;
+    rc = lower_plan(h);
     if (rc != UMX_OK) { umx_destroy(h); return rc; }
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -543,7 +662,7 @@ int umx_create(const umx_model_desc* desc, const umx_tensor* weights, int32_t n_
         cudaEventCreateWithFlags(&h->ev_stitch[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming);
     }
-    if (conv_simt_configure() != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError())); umx_destroy(h); return UMX_ECUDA; }
+    if (conv_simt_configure() != cudaSuccess || tc_conv_configure() != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError())); umx_destroy(h); return UMX_ECUDA; }
     h->tensors.clear();   // host copies no longer needed
     *out = h;
     return UMX_OK;
@@ -557,7 +676,7 @@ void umx_destroy(umx_handle* h) {
     drain_profile(h);
     for (auto e : h->event_pool) cudaEventDestroy(e);
     for (auto p : h->dev_allocs) cudaFree(p);
-    for (auto& b : h->bufs) if (b.d) cudaFree(b.d);
+    for (auto& b : h->bufs) { if (b.d) cudaFree(b.d); if (b.dh) cudaFree(b.dh); }
     if (h->probs) cudaFree(h->probs);
     if (h->d_img) cudaFree(h->d_img);
     if (h->d_probs_rows) cudaFree(h->d_probs_rows);
@@ -603,6 +722,29 @@ int umx_profile_read(umx_handle* h, umx_prof_entry* out, int32_t capacity, int32
 }
 
 int64_t umx_launch_count(umx_handle* h) { return h ? h->launches : 0; }
+
+int64_t umx_debug_buffer(umx_handle* h, const char* name, int32_t n_tiles, float* out, int64_t capacity) {
+    if (!h || !name || !out || n_tiles < 0) { set_error("umx_debug_buffer: bad argument"); return UMX_EINVAL; }
+    UMX_CUDA_TRY(cudaSetDevice(h->device));
+    for (auto& b : h->bufs) {
+        if (b.name != name) continue;
+        const int64_t n = (int64_t)std::min(n_tiles, h->cap_tiles) * b.per_tile();
+        if (n > capacity) { set_error("umx_debug_buffer: capacity %lld < %lld", (long long)capacity, (long long)n); return UMX_EINVAL; }
+        UMX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        if (b.d) {
+            UMX_CUDA_TRY(cudaMemcpy(out, b.d, n * sizeof(float), cudaMemcpyDeviceToHost));
+        } else if (b.dh) {
+            std::vector<__half> tmp(n);
+            for (int pl = 0; pl < b.planes; ++pl) {
+                UMX_CUDA_TRY(cudaMemcpy(tmp.data(), b.dh + pl * b.plane_elems, n * sizeof(__half), cudaMemcpyDeviceToHost));
+                for (int64_t i = 0; i < n; ++i) out[i] = (pl ? out[i] : 0.f) + __half2float(tmp[i]);
+            }
+        } else { set_error("buffer '%s' is not materialised", name); return UMX_EINVAL; }
+        return b.per_tile();
+    }
+    set_error("no buffer named '%s'", name);
+    return UMX_EINVAL;
+}
 
 int umx_forward_tiles(umx_handle* h, const float* tiles, int32_t n_tiles, float* probs, int32_t precision) {
     (void)precision;

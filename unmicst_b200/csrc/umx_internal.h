@@ -9,6 +9,7 @@
 
 #include "../../include/unmicst_b200.h"
 #include "umx_kernels.cuh"
+#include "umx_tc.cuh"
 
 namespace umx {
 
@@ -35,12 +36,32 @@ struct HostTensor {
     int64_t numel() const { int64_t n = 1; for (auto d : shape) n *= d; return n; }
 };
 
-// A per-tile activation buffer living in the workspace (fp32 NHWC).
+// A per-tile activation buffer living in the workspace (NHWC); fp32 and/or fp16 hi[/lo] planes,
+// depending on which kernels consume it.
 struct Buffer {
     std::string name;
     int h = 0, w = 0, c = 0;
-    float* d = nullptr;             // [max_batch][h][w][c]
+    bool need_f = false, need_h = false;
+    float* d = nullptr;             // [cap][h][w][c] fp32
+    __half* dh = nullptr;           // [planes][cap][h][w][c] fp16
+    int planes = 0;
+    int64_t plane_elems = 0;
     int64_t per_tile() const { return (int64_t)h * w * c; }
+};
+
+struct TermHost {
+    int src0 = -1, src1 = -1;         // buffer ids (src1: second concat source)
+    std::vector<float> w;             // fp32 [tap][c0+c1][cout], BN scale folded where the graph allows
+    int k = 3;
+};
+
+struct ConvSpec {
+    std::vector<TermHost> terms;
+    int cout = 0;
+    bool transpose = false;
+    bool has_bias = false, has_post = false, pool = false;
+    std::vector<float> bias, post_scale, post_shift;
+    int act = 0;
 };
 
 enum OpKind { OP_CONV = 0, OP_TOP = 1 };
@@ -48,14 +69,17 @@ enum OpKind { OP_CONV = 0, OP_TOP = 1 };
 struct Op {
     OpKind kind = OP_CONV;
     std::string name;
-    // OP_CONV (conv and conv-transpose, fp32 CUDA-core implementation)
-    ConvParams cp{};                 // device pointers filled at plan time; n_tiles patched per launch
-    // OP_TOP
+    ConvSpec spec;
+    bool use_tc = false;
+    ConvParams cp{};                 // fp32 CUDA-core implementation
+    TcConvParams tcp{};              // tcgen05 implementation
+    alignas(64) CUtensorMap mapA0, mapA1, mapB;
     TopParams tp{};
+    std::vector<float> top_w, top_b;
     int top_src = -1;
     int out_buf = -1;
     double flops_per_tile = 0;       // algorithmic (2*MAC)
-    double bytes_per_tile = 0;       // activations read + written once, fp32
+    double bytes_per_tile = 0;       // activations read + written once at 4 B/element
     double weight_bytes = 0;         // per launch
     int prof_slot = -1;
 };
@@ -79,6 +103,9 @@ struct umx_handle {
     umx_model_desc desc{};
     int S = 0, C = 0, K = 0, L = 0, margin = 0, sub = 0;
     int max_batch = 0;
+    int cap_tiles = 0;                           // workspace capacity in tiles (max_batch rounded up to 8)
+    int num_sms = 148;
+    int precision = UMX_PREC_SPLIT3;
     std::vector<int> chan;                       // nOutX
     std::map<std::string, umx::HostTensor> tensors;
     std::vector<float*> dev_allocs;              // weights etc.

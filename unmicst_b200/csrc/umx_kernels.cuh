@@ -1,6 +1,7 @@
 // Kernel-facing parameter blocks and launch wrappers shared between the kernel
 // translation units and the C-ABI (umx_api.cu).  Device code only sees PODs.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -42,7 +43,10 @@ struct ConvParams {
     const float* bias;          // [cout] or nullptr
     const float* post_scale;    // [cout] affine applied after the activation (legacy BN) or nullptr
     const float* post_shift;
-    float* out;                 // NHWC fp32
+    float* out;                 // NHWC fp32 or nullptr
+    __half* out_h;              // fp16 hi[/lo] planes [out_planes][n][oh][ow][cout] for tensor-path consumers, or nullptr
+    int64_t out_plane_elems;
+    int32_t out_planes;
 };
 
 struct TopParams {              // lt 1x1 conv (+ folded BN) + softmax over K classes

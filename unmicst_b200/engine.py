@@ -202,6 +202,17 @@ class Engine:
         return [dict(name=buf[i].name.decode(), launches=int(buf[i].launches), ms=float(buf[i].ms_total),
                      flops=float(buf[i].flops), bytes=float(buf[i].bytes)) for i in range(min(n, cap))]
 
+    def debug_buffer(self, name: str, n_tiles: int, shape_hwc: Tuple[int, int, int]) -> np.ndarray:
+        """Activation written by op ``name`` during the last forward, as fp32 [n,h,w,c] (bring-up aid)."""
+        hh, ww, cc = shape_hwc
+        out = np.empty((n_tiles, hh, ww, cc), dtype=np.float32)
+        r = lib().umx_debug_buffer(self._h, name.encode(), n_tiles, out.ctypes.data, out.size)
+        if r < 0:
+            check(int(r))
+        if r != hh * ww * cc:
+            raise ValueError(f"buffer {name} has {r} elements per tile, expected {hh * ww * cc}")
+        return out
+
     @property
     def launch_count(self) -> int:
         return int(lib().umx_launch_count(self._h))
