@@ -218,6 +218,83 @@ __global__ void __launch_bounds__(NTHR) conv_simt_kernel(const __grid_constant__
     }
 }
 
+// Block: one 32x32-pixel region of one tile (16x16 pooled pixels); thread: one pooled pixel, all
+// output channels in groups of 16.  Weights are read from shared memory as warp-wide broadcasts.
+template <int CIN>
+__global__ void __launch_bounds__(256) first_conv_kernel(const FirstParams p) {
+    extern __shared__ __align__(16) float smem[];
+    float* xin = smem;                                   // [34][34][CIN]
+    float* ws = smem + ((34 * 34 * CIN + 3) & ~3);       // [9][CIN][cout]
+    float* bs = ws + 9 * CIN * p.cout;                   // [cout]
+    const int nb = p.S / 32;
+    const int n = blockIdx.x / (nb * nb);
+    const int rb = blockIdx.x % (nb * nb);
+    const int y0 = (rb / nb) * 32, x0 = (rb % nb) * 32;
+    for (int i = threadIdx.x; i < 34 * 34; i += 256) {
+        const int r = i / 34, c = i % 34;
+        const int gy = y0 + r - 1, gx = x0 + c - 1;
+        const bool inb = gy >= 0 && gy < p.S && gx >= 0 && gx < p.S;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci)
+            xin[i * CIN + ci] = inb ? __ldg(p.src + (((int64_t)n * p.S + gy) * p.S + gx) * CIN + ci) : 0.f;
+    }
+    for (int i = threadIdx.x; i < 9 * CIN * p.cout; i += 256) ws[i] = __ldg(p.w + i);
+    for (int i = threadIdx.x; i < p.cout; i += 256) bs[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+    __syncthreads();
+    const int py = threadIdx.x >> 4, px = threadIdx.x & 15;
+    float in[4][4][CIN];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) in[a][b][ci] = xin[((2 * py + a) * 34 + 2 * px + b) * CIN + ci];
+    const int oh = p.S / 2;
+    const int64_t opix = ((int64_t)n * oh + (y0 / 2 + py)) * oh + (x0 / 2 + px);
+    for (int cg = 0; cg < p.cout; cg += 16) {
+        float acc[4][16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[q][j] = bs[cg + j];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap % 3;
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) {
+                const float4* w4 = reinterpret_cast<const float4*>(ws + (tap * CIN + ci) * p.cout + cg);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 w = w4[j4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float xv = in[(q >> 1) + dy][(q & 1) + dx][ci];
+                        acc[q][j4 * 4 + 0] = fmaf(xv, w.x, acc[q][j4 * 4 + 0]);
+                        acc[q][j4 * 4 + 1] = fmaf(xv, w.y, acc[q][j4 * 4 + 1]);
+                        acc[q][j4 * 4 + 2] = fmaf(xv, w.z, acc[q][j4 * 4 + 2]);
+                        acc[q][j4 * 4 + 3] = fmaf(xv, w.w, acc[q][j4 * 4 + 3]);
+                    }
+                }
+            }
+        }
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            v[j] = fmaxf(fmaxf(apply_act(acc[0][j], p.act, p.leaky), apply_act(acc[1][j], p.act, p.leaky)),
+                         fmaxf(apply_act(acc[2][j], p.act, p.leaky), apply_act(acc[3][j], p.act, p.leaky)));
+        const int64_t oo = opix * p.cout + cg;
+        if (p.out) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4)
+                reinterpret_cast<float4*>(p.out + oo)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+        }
+        if (p.out_h) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) store_h2x4(p.out_h + oo + j4 * 4, p.out_plane_elems, p.out_planes, v + j4 * 4);
+        }
+    }
+}
+
 // One thread per pixel: K logits from cin channels, then a numerically stable softmax.
 template <int K>
 __global__ void __launch_bounds__(256) top_softmax_kernel(const TopParams p) {
@@ -385,6 +462,17 @@ cudaError_t launch_top_softmax(const TopParams& p, cudaStream_t s) {
     if (p.k == 2) top_softmax_kernel<2><<<blocks, 256, sm, s>>>(p);
     else if (p.k == 3) top_softmax_kernel<3><<<blocks, 256, sm, s>>>(p);
     else if (p.k == 4) top_softmax_kernel<4><<<blocks, 256, sm, s>>>(p);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_first_conv(const FirstParams& p, cudaStream_t s) {
+    if (p.n_tiles == 0) return cudaSuccess;
+    const int nb = p.S / 32;
+    const unsigned grid = (unsigned)p.n_tiles * nb * nb;
+    const size_t sm = (((size_t)34 * 34 * p.cin + 3) & ~(size_t)3) * 4 + ((size_t)9 * p.cin * p.cout + p.cout) * 4;
+    if (p.cin == 1) first_conv_kernel<1><<<grid, 256, sm, s>>>(p);
+    else if (p.cin == 2) first_conv_kernel<2><<<grid, 256, sm, s>>>(p);
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }

@@ -119,6 +119,8 @@ __device__ __forceinline__ float act_fn(float v, int act, float leaky) {
     return v;
 }
 
+// SKIPC = channels of the narrow fp32 skip source folded into the epilogue (0 = none).
+template <int SKIPC>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ TcConvParams p) {
@@ -134,6 +136,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const uint32_t tfull0 = empty0 + 8 * p.stages;
     const uint32_t tempty0 = tfull0 + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+    // small fp32 tables for the epilogue: skip-term weights [9][SKIPC][cout], lt weights [cout][K], lt bias [K]
+    float* s_skipw = reinterpret_cast<float*>(tmem_slot + 4);
+    float* s_topw = s_skipw + 9 * SKIPC * p.cout;
+    float* s_topb = s_topw + (p.top_w ? p.cout * p.top_k : 0);
+    if (SKIPC > 0)
+        for (int i = threadIdx.x; i < 9 * SKIPC * p.cout; i += kThreads) s_skipw[i] = p.skip_w[i];
+    if (p.top_w) {
+        for (int i = threadIdx.x; i < p.cout * p.top_k; i += kThreads) s_topw[i] = p.top_w[i];
+        if (threadIdx.x < p.top_k) s_topb[threadIdx.x] = p.top_b ? p.top_b[threadIdx.x] : 0.f;
+    }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -240,6 +252,20 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             else if (p.os == 2) { oh = p.in_h * 2; ow = p.in_w * 2; oy = 2 * y + (t.phase >> 1); ox = 2 * x + (t.phase & 1); }
             else { oh = p.in_h; ow = p.in_w; oy = y; ox = x; }
             const int64_t opix = ((int64_t)n * oh + oy) * ow + ox;
+            // narrow fp32 skip source (raw input channels of lu0.conv2): its 3x3 neighbourhood in registers
+            float xs[9 * (SKIPC > 0 ? SKIPC : 1)];
+            if (SKIPC > 0) {
+#pragma unroll
+                for (int tp = 0; tp < 9; ++tp) {
+                    const TcTap tap = p.taps[0][tp];
+                    const int yy = y + tap.dy, xx = x + tap.dx;
+                    const bool inb = valid && yy >= 0 && yy < p.in_h && xx >= 0 && xx < p.in_w;
+#pragma unroll
+                    for (int cs = 0; cs < SKIPC; ++cs)
+                        xs[tp * SKIPC + cs] = inb ? __ldg(p.skip_src + (((int64_t)n * p.in_h + yy) * p.in_w + xx) * SKIPC + cs) : 0.f;
+                }
+            }
+            float z[4] = {0.f, 0.f, 0.f, 0.f};           // fused lt logits
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
@@ -252,7 +278,35 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 for (int j = 0; j < 16; ++j) {
                     float b = 0.f;
                     if (p.bias && co + j < p.cout) b = __ldg(p.bias + co + j);
-                    v[j] = act_fn(__uint_as_float(r[j]) + b, p.act, p.leaky);
+                    v[j] = __uint_as_float(r[j]) + b;
+                }
+                if (SKIPC > 0 && co + 16 <= p.cout) {
+#pragma unroll
+                    for (int tp = 0; tp < 9; ++tp) {
+                        const int wi = p.taps[0][tp].wi;
+#pragma unroll
+                        for (int cs = 0; cs < SKIPC; ++cs) {
+                            const float xv = xs[tp * SKIPC + cs];
+                            const float4* w4 = reinterpret_cast<const float4*>(s_skipw + (wi * SKIPC + cs) * p.cout + co);
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const float4 w = w4[j4];
+                                v[j4 * 4 + 0] = fmaf(xv, w.x, v[j4 * 4 + 0]); v[j4 * 4 + 1] = fmaf(xv, w.y, v[j4 * 4 + 1]);
+                                v[j4 * 4 + 2] = fmaf(xv, w.z, v[j4 * 4 + 2]); v[j4 * 4 + 3] = fmaf(xv, w.w, v[j4 * 4 + 3]);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = act_fn(v[j], p.act, p.leaky);
+                if (p.top_w && co + 16 <= p.cout) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float* wk = s_topw + (co + j) * p.top_k;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (k < p.top_k) z[k] = fmaf(v[j], wk[k], z[k]);
+                    }
                 }
                 if (p.pool) {
 #pragma unroll
@@ -285,6 +339,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     }
                 }
                 __syncwarp();        // reconverge before the next .sync.aligned TMEM load
+            }
+            if (p.top_w && writer) {
+                float mx = -INFINITY, sum = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (k < p.top_k) { z[k] += s_topb[k]; mx = fmaxf(mx, z[k]); }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (k < p.top_k) { z[k] = expf(z[k] - mx); sum += z[k]; }
+                const float inv = 1.f / sum;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (k < p.top_k) p.top_probs[opix * p.top_k + k] = z[k] * inv;
             }
             tc_fence_before();
             __syncwarp();
@@ -320,11 +384,15 @@ EncodeTiledFn encode_fn() {
 
 size_t tc_conv_smem_bytes(const TcConvParams& p) {
     const size_t stage = (size_t)p.planes * (kAPlaneBytes + (size_t)p.n_t * 128);
-    return (size_t)p.stages * stage + (2 * p.stages + 4) * 8 + 16 + 1024;
+    const size_t tables = ((size_t)9 * p.skip_c * p.cout + (p.top_w ? (size_t)p.cout * p.top_k + 4 : 0)) * sizeof(float);
+    return (size_t)p.stages * stage + (2 * p.stages + 4) * 8 + 16 + tables + 1024;
 }
 
 cudaError_t tc_conv_configure() {
-    return cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return e;
 }
 
 cudaError_t launch_tc_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcConvParams& p,
@@ -336,7 +404,12 @@ cudaError_t launch_tc_conv(const CUtensorMap& a0, const CUtensorMap& a1, const C
     // at least ~120 KB so that exactly one CTA (and its 512 TMEM columns) lives on an SM
     size_t smem = tc_conv_smem_bytes(p);
     if (smem < 120 * 1024) smem = 120 * 1024;
-    tc_conv_kernel<<<grid, kThreads, smem, s>>>(a0, a1, b, p);
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    const int skipc = p.skip_src ? p.skip_c : 0;
+    if (skipc == 0) tc_conv_kernel<0><<<grid, kThreads, smem, s>>>(a0, a1, b, p);
+    else if (skipc == 1) tc_conv_kernel<1><<<grid, kThreads, smem, s>>>(a0, a1, b, p);
+    else if (skipc == 2) tc_conv_kernel<2><<<grid, kThreads, smem, s>>>(a0, a1, b, p);
+    else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 

@@ -313,12 +313,24 @@ int build_plan(umx_handle* h) {
     return UMX_OK;
 }
 
+// lu0.conv2 pattern: concat(raw input with <= 2 channels, wide up tensor) -> the wide part runs on the
+// tensor cores, the narrow part is a handful of fp32 FMAs per output in the epilogue.
+bool tc_skip_mode(const umx_handle* h, const Op& op) {
+    const ConvSpec& sp = op.spec;
+    if (sp.terms.size() != 1 || sp.terms[0].src1 < 0 || sp.transpose || sp.pool) return false;
+    const Buffer& a = h->bufs[sp.terms[0].src0];
+    const Buffer& b = h->bufs[sp.terms[0].src1];
+    return a.c <= 2 && b.c % 8 == 0 && sp.cout % 16 == 0;
+}
+
 bool tc_eligible(const umx_handle* h, const Op& op) {
     if (h->precision == UMX_PREC_FP32 || op.kind != OP_CONV) return false;
     const ConvSpec& sp = op.spec;
     if (sp.terms.size() != 1 || sp.has_post || sp.terms[0].k != 3) return false;
     const Buffer& a = h->bufs[sp.terms[0].src0];
-    if (a.c % 8 != 0 || sp.cout % 8 != 0 || a.h < 4 || a.w < 4) return false;
+    if (sp.cout % 8 != 0 || a.h < 4 || a.w < 4) return false;
+    if (tc_skip_mode(h, op)) return true;
+    if (a.c % 8 != 0) return false;
     if (sp.terms[0].src1 >= 0 && h->bufs[sp.terms[0].src1].c % 8 != 0) return false;
     return true;
 }
@@ -379,13 +391,36 @@ int lower_conv_simt(umx_handle* h, Op& op) {
     return UMX_OK;
 }
 
+bool first_eligible(const umx_handle* h, const Op& op) {
+    if (op.kind != OP_CONV) return false;
+    const ConvSpec& sp = op.spec;
+    if (sp.terms.size() != 1 || sp.has_post || sp.terms[0].k != 3 || sp.terms[0].src1 >= 0 || sp.transpose || !sp.pool) return false;
+    const Buffer& a = h->bufs[sp.terms[0].src0];
+    return a.c <= 2 && sp.cout % 16 == 0 && a.h % 32 == 0 && a.h == a.w && (9 * a.c * sp.cout + sp.cout + 34 * 34 * a.c + 4) * 4 <= 48 * 1024;
+}
+
+int lower_conv_first(umx_handle* h, Op& op) {
+    const ConvSpec& sp = op.spec;
+    FirstParams& fp = op.fp;
+    memset(&fp, 0, sizeof(fp));
+    const Buffer& a = h->bufs[sp.terms[0].src0];
+    if (!a.d) { set_error("%s: fp32 source buffer missing", op.name.c_str()); return UMX_EINVAL; }
+    fp.src = a.d; fp.S = a.h; fp.cin = a.c; fp.cout = sp.cout; fp.act = sp.act; fp.leaky = kLeaky;
+    float* d = nullptr;
+    UMX_TRY(upload(h, sp.terms[0].w, &d)); fp.w = d;
+    if (sp.has_bias) { UMX_TRY(upload(h, sp.bias, &d)); fp.bias = d; }
+    const Buffer& ob = h->bufs[op.out_buf];
+    fp.out = ob.d; fp.out_h = ob.dh; fp.out_planes = ob.planes; fp.out_plane_elems = ob.plane_elems;
+    return UMX_OK;
+}
+
 int lower_conv_tc(umx_handle* h, Op& op) {
     const ConvSpec& sp = op.spec;
     TcConvParams& tp = op.tcp;
     memset(&tp, 0, sizeof(tp));
     const TermHost& T = sp.terms[0];
-    const Buffer& a0 = h->bufs[T.src0];
-    const Buffer* a1 = T.src1 >= 0 ? &h->bufs[T.src1] : nullptr;
+    const Buffer& a0 = h->bufs[op.skip_mode ? T.src1 : T.src0];
+    const Buffer* a1 = (!op.skip_mode && T.src1 >= 0) ? &h->bufs[T.src1] : nullptr;
     const int planes = h->precision == UMX_PREC_SINGLE ? 1 : 2;
     tp.in_h = a0.h; tp.in_w = a0.w;
     tp.bw = std::min(a0.w, 16); tp.bh = std::min(a0.h, 128 / tp.bw); tp.bn = 128 / (tp.bw * tp.bh);
@@ -409,8 +444,31 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     tp.out_f = ob.d; tp.out_h = ob.dh; tp.out_planes = ob.planes; tp.out_plane_elems = ob.plane_elems;
     // weights -> fp16 planes on the device
     const int cin = tp.c0 + tp.c1;
+    std::vector<float> wmain = T.w;
+    if (op.skip_mode) {
+        const Buffer& sk = h->bufs[T.src0];
+        const int cs = sk.c, ctot = cs + cin;
+        std::vector<float> wskip((size_t)9 * cs * sp.cout);
+        wmain.assign((size_t)9 * cin * sp.cout, 0.f);
+        for (int t = 0; t < 9; ++t)
+            for (int i = 0; i < ctot; ++i)
+                for (int o = 0; o < sp.cout; ++o) {
+                    const float v = T.w[((size_t)t * ctot + i) * sp.cout + o];
+                    if (i < cs) wskip[((size_t)t * cs + i) * sp.cout + o] = v;
+                    else wmain[((size_t)t * cin + (i - cs)) * sp.cout + o] = v;
+                }
+        UMX_TRY(upload(h, wskip, &d));
+        tp.skip_w = d; tp.skip_c = cs; tp.skip_src = sk.d;
+        if (!sk.d) { set_error("%s: fp32 skip source missing", op.name.c_str()); return UMX_EINVAL; }
+    }
+    if (op.fuse_top >= 0) {
+        Op& top = h->ops[op.fuse_top];
+        UMX_TRY(upload(h, top.top_w, &d)); tp.top_w = d;
+        if (!top.top_b.empty()) { UMX_TRY(upload(h, top.top_b, &d)); tp.top_b = d; }
+        tp.top_k = h->K;
+    }
     std::vector<__half> wh;
-    split_weights(T.w, 9, cin, sp.cout, planes, &wh);
+    split_weights(wmain, 9, cin, sp.cout, planes, &wh);
     __half* dw = nullptr;
     UMX_CUDA_TRY(cudaMalloc(&dw, wh.size() * sizeof(__half)));
     h->dev_allocs.push_back(reinterpret_cast<float*>(dw));
@@ -432,16 +490,36 @@ int lower_conv_tc(umx_handle* h, Op& op) {
 // Decide per op which kernel runs it, which formats every buffer must exist in, allocate the
 // workspace and bind device pointers / tensor maps.
 int lower_plan(umx_handle* h) {
-    for (auto& op : h->ops) {
+    for (size_t i = 0; i < h->ops.size(); ++i) {
+        Op& op = h->ops[i];
         op.use_tc = tc_eligible(h, op);
+        op.skip_mode = op.use_tc && tc_skip_mode(h, op);
+        op.use_first = !op.use_tc && first_eligible(h, op);
+    }
+    // lt 1x1 conv + softmax rides in the epilogue of the conv that feeds it when one CTA tile spans all channels
+    for (size_t i = 1; i < h->ops.size(); ++i) {
+        Op& top = h->ops[i];
+        Op& prev = h->ops[i - 1];
+        if (top.kind == OP_TOP && prev.kind == OP_CONV && prev.use_tc && prev.out_buf == top.top_src &&
+            prev.spec.cout % 16 == 0 && pick_n_tile(prev.spec.cout) == prev.spec.cout && !prev.spec.pool && !prev.spec.transpose) {
+            prev.fuse_top = (int)i;
+            top.fused_away = true;
+            const Buffer& ob = h->bufs[prev.out_buf];
+            prev.flops_per_tile += top.flops_per_tile;
+            prev.bytes_per_tile += 4.0 * ob.h * ob.w * (h->K - ob.c);     // writes K probabilities instead of cout activations
+            prev.name += "+lt";
+        }
+    }
+    for (auto& op : h->ops) {
         if (op.kind == OP_CONV) {
             for (auto& t : op.spec.terms) {
+                if (op.skip_mode) { h->bufs[t.src0].need_f = true; h->bufs[t.src1].need_h = true; continue; }
                 for (int s : {t.src0, t.src1}) {
                     if (s < 0) continue;
                     if (op.use_tc) h->bufs[s].need_h = true; else h->bufs[s].need_f = true;
                 }
             }
-        } else {
+        } else if (!op.fused_away) {
             h->bufs[op.top_src].need_f = true;
         }
     }
@@ -458,9 +536,11 @@ int lower_plan(umx_handle* h) {
     UMX_CUDA_TRY(cudaMalloc(&h->probs, (size_t)h->cap_tiles * h->S * h->S * h->K * sizeof(float)));
     for (auto& op : h->ops) {
         if (op.kind == OP_CONV) {
-            if (op.use_tc) UMX_TRY(lower_conv_tc(h, op)); else UMX_TRY(lower_conv_simt(h, op));
+            if (op.use_tc) UMX_TRY(lower_conv_tc(h, op));
+            else if (op.use_first) UMX_TRY(lower_conv_first(h, op));
+            else UMX_TRY(lower_conv_simt(h, op));
             op.spec = ConvSpec();       // host copies of the weights are no longer needed
-        } else {
+        } else if (!op.fused_away) {
             float* d = nullptr;
             UMX_TRY(upload(h, op.top_w, &d)); op.tp.w = d;
             if (!op.top_b.empty()) { UMX_TRY(upload(h, op.top_b, &d)); op.tp.bias = d; }
@@ -515,11 +595,17 @@ void drain_profile(umx_handle* h) {
 // Run the network on nb tiles already sitting in the input buffer; probs -> `probs_out` (device).
 int run_network(umx_handle* h, int nb, float* probs_out) {
     for (auto& op : h->ops) {
+        if (op.fused_away) continue;
         ScopedTimer tm(h, op.prof_slot, op.flops_per_tile * nb, op.bytes_per_tile * nb + op.weight_bytes);
         if (op.kind == OP_CONV && op.use_tc) {
             TcConvParams tp = op.tcp;
             tp.n_tiles = nb;
+            if (op.fuse_top >= 0) tp.top_probs = probs_out;
             UMX_CUDA_TRY(launch_tc_conv(op.mapA0, op.mapA1, op.mapB, tp, h->num_sms, h->stream));
+        } else if (op.kind == OP_CONV && op.use_first) {
+            FirstParams fp = op.fp;
+            fp.n_tiles = nb;
+            UMX_CUDA_TRY(launch_first_conv(fp, h->stream));
         } else if (op.kind == OP_CONV) {
             ConvParams cp = op.cp;
             cp.n_tiles = nb;

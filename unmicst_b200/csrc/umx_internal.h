@@ -71,6 +71,11 @@ struct Op {
     std::string name;
     ConvSpec spec;
     bool use_tc = false;
+    bool use_first = false;          // dedicated first-layer kernel (1-2 input channels, 3x3, pooled)
+    FirstParams fp{};
+    bool skip_mode = false;          // tensor path with the narrow first concat source folded into the epilogue
+    int fuse_top = -1;               // index of the OP_TOP fused into this conv's epilogue
+    bool fused_away = false;         // OP_TOP executed inside the preceding conv
     ConvParams cp{};                 // fp32 CUDA-core implementation
     TcConvParams tcp{};              // tcgen05 implementation
     alignas(64) CUtensorMap mapA0, mapA1, mapB;

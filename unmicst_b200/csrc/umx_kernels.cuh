@@ -49,6 +49,21 @@ struct ConvParams {
     int32_t out_planes;
 };
 
+// First layer of the v2 graphs: 3x3 SAME conv from 1 or 2 input channels + bias + activation +
+// 2x2 max-pool, straight from the normalised tile to the pooled fp16/fp32 feature map.
+struct FirstParams {
+    const float* src;           // [n][S][S][cin]
+    const float* w;             // [9][cin][cout] fp32 (BN scale folded)
+    const float* bias;          // [cout]
+    int32_t n_tiles, S, cin, cout;
+    int32_t act;
+    float leaky;
+    float* out;                 // [n][S/2][S/2][cout] fp32 or nullptr
+    __half* out_h;              // fp16 hi[/lo] planes or nullptr
+    int64_t out_plane_elems;
+    int32_t out_planes;
+};
+
 struct TopParams {              // lt 1x1 conv (+ folded BN) + softmax over K classes
     const float* src;           // [n_pix][cin]
     const float* w;             // [cin][K]
@@ -96,6 +111,7 @@ struct StitchParams {           // PI2D.patchOutput/getValidOutput as a gather +
 // launchers (kernels_simt.cu)
 cudaError_t launch_conv_simt(const ConvParams& p, cudaStream_t s);
 cudaError_t launch_top_softmax(const TopParams& p, cudaStream_t s);
+cudaError_t launch_first_conv(const FirstParams& p, cudaStream_t s);
 cudaError_t launch_gather_tiles(const GatherParams& p, cudaStream_t s);
 cudaError_t launch_stitch(const StitchParams& p, cudaStream_t s);
 cudaError_t conv_simt_configure();   // opt in to > 48 KB dynamic shared memory
