@@ -1,0 +1,131 @@
+"""Host-side logic that needs no GPU: tile geometry/band sharding, CLI flag mapping and naming,
+pre/post-processing against the oracle restatement, TIFF round trips."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pi2d_oracle, prepost_oracle
+from unmicst_b200 import cli, prepost, tiffio
+from unmicst_b200.engine import split_tile_rows, tile_geometry
+
+
+@pytest.mark.parametrize("H,W,S", [(832, 960, 128), (20000, 20000, 64), (1, 1, 64), (4096, 4096, 128), (18432, 30720, 256)])
+def test_tile_geometry_matches_pi2d(H, W, S):
+    m, sub, npr, npc = tile_geometry(H, W, S)
+    g = pi2d_oracle.tile_grid(H, W, S, int(S / 8))
+    assert (m, sub, npr, npc) == (g.margin, g.sub, g.npr, g.npc)
+
+
+def test_reference_tile_counts():
+    """90 tiles @128 / 360 @64 for 832x960; 173 889 @64 for 20k^2; 1 849 @128 for 4096^2."""
+    cnt = lambda H, W, S: (lambda t: t[2] * t[3])(tile_geometry(H, W, S))
+    assert cnt(832, 960, 128) == 90 and cnt(832, 960, 64) == 360
+    assert cnt(20000, 20000, 64) == 173889 and cnt(4096, 4096, 128) == 1849 and cnt(40000, 40000, 64) == 695556
+
+
+@pytest.mark.parametrize("npr,parts", [(417, 8), (9, 2), (3, 8), (1, 4), (100, 1)])
+def test_band_split_is_a_partition(npr, parts):
+    bands = split_tile_rows(npr, parts)
+    assert bands[0][0] == 0 and bands[-1][1] == npr
+    assert all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+    sizes = [b - a for a, b in bands]
+    assert min(sizes) >= 1 and max(sizes) - min(sizes) <= 1
+
+
+def test_wrapper_converts_to_zero_based():
+    a = cli.wrapper_parser().parse_args(["img.ome.tif", "--channel", "3", "--classOrder", "1", "2", "3", "--GPU", "2",
+                                         "--stackOutput", "--outputPath", "out"])
+    tool, argv = cli.wrapper_to_tool_argv(a)
+    assert tool == "unmicst-solo"
+    t = cli.tool_parser(cli.TOOLS[tool]).parse_args(argv)
+    assert t.channel == ["2"] and t.classOrder == [0, 1, 2] and t.GPU == 1 and t.stackOutput and t.outputPath == "out"
+    assert t.model == "nucleiDAPI1-5" and t.mean == -1 and t.scalingFactor == 1
+
+
+def test_wrapper_tool_dispatch_and_defaults():
+    for tool, model in (("unmicst-duo", "nucleiDAPILAMIN"), ("unmicst-legacy", "nucleiDAPI"), ("UnMicstCyto2", "CytoplasmIncell2")):
+        a = cli.wrapper_parser().parse_args(["x.tif", "--tool", tool, "--channel", "1", "2"])
+        got, argv = cli.wrapper_to_tool_argv(a)
+        assert got == tool
+        t = cli.tool_parser(cli.TOOLS[tool]).parse_args(argv)
+        assert t.model == model and t.GPU == -1
+        if tool == "unmicst-duo":
+            assert t.channel == ["0", "1"]
+    a = cli.wrapper_parser().parse_args(["x.tif"])
+    assert "--outputPath" not in cli.wrapper_to_tool_argv(a)[1]       # quirk Q7 fixed: no literal 'None'
+
+
+def test_file_stem_rules():
+    assert cli.split_name("exemplar-001-cycle6.ome.tif", True) == ("exemplar-001-cycle6", "ome.tif")
+    assert cli.split_name("a.b.tif", True) == ("a.b", "tif")
+    assert cli.split_name("a.b.tif", False) == ("a", "b.tif")          # legacy/duo/Cyto2 split at the first dot
+    with pytest.raises(NotImplementedError):
+        cli.split_name("noext", True)
+    with pytest.raises(NotImplementedError):
+        cli.read_channel("x.xyz", "xyz", 0)
+
+
+def _apply(arr, pm):
+    x = arr.astype(np.float64) * pm.in_scale
+    if pm.rescale:
+        x = np.clip(x, pm.imin, pm.imax)
+        x = (x - pm.imin) / (pm.imax - pm.imin) * (pm.omax - pm.omin) + pm.omin
+    return x
+
+
+def test_network_input_matches_oracle_preprocessing(sample_raw):
+    arr, pm = prepost.network_input(sample_raw, 1.0, stretch=True)
+    assert arr.dtype == np.uint16                                      # integers go to the GPU untouched
+    assert np.array_equal(_apply(arr, pm), prepost_oracle.prepare_rescaled(sample_raw))
+    arr, pm = prepost.network_input(sample_raw, 1.0, stretch=False)
+    assert np.array_equal(_apply(arr, pm), prepost_oracle.prepare_solo(sample_raw))
+    crop = sample_raw[:200, :300]
+    for f in (2.0, 0.5):
+        arr, pm = prepost.network_input(crop, f, stretch=True, outlier=99.0)
+        assert arr.shape == (int(200 * f), int(300 * f))
+        assert np.allclose(_apply(arr, pm), prepost_oracle.prepare_rescaled(crop, f, 99.0), atol=1e-12)
+
+
+def test_requantisation_table_and_preview(sample_raw, sample_goldens):
+    v = np.arange(256, dtype=np.uint8).reshape(16, 16)
+    want = np.uint8(255 * prepost_oracle.resize(v, (16, 16)))
+    assert np.array_equal(prepost.back_to_raw_size(v, (16, 16)), want)
+    assert np.abs(want.astype(int) - v.astype(int)).max() <= 1
+    assert np.array_equal(prepost.preview_page(sample_raw), sample_goldens["raw"])
+
+
+def test_tiff_roundtrip_append_and_golden_pages(tmp_path, golden_dir, sample_goldens):
+    rng = np.random.default_rng(0)
+    pages = [rng.integers(0, 255, (77, 131), dtype=np.uint8) for _ in range(3)]
+    for big in (True, False):
+        p = str(tmp_path / f"s{big}.tif")
+        for i, pg in enumerate(pages):
+            tiffio.imsave(p, pg, append=i > 0, bigtiff=big)
+        assert tiffio.count_pages(p) == 3
+        assert all(np.array_equal(tiffio.read_page(p, i), pages[i]) for i in range(3))
+        from PIL import Image
+        im = Image.open(p)
+        assert im.n_frames == 3
+    g = os.path.join(golden_dir, "sample", "105_ContoursPM_1.tif")
+    assert tiffio.count_pages(g) == 2
+    assert np.array_equal(tiffio.read_page(g, 0), sample_goldens["contours"])
+    assert np.array_equal(tiffio.read_page(g, 1), sample_goldens["raw"])
+    with pytest.raises(IndexError):
+        tiffio.read_page(g, 2)
+    x16 = rng.integers(0, 65535, (40, 50), dtype=np.uint16)
+    p = str(tmp_path / "u16.tif")
+    with tiffio.BigTiffWriter(p) as w:                                   # streamed page, band by band
+        w.begin_page(40, 50, np.uint16)
+        w.write_rows(x16[:13]); w.write_rows(x16[13:])
+        w.end_page()
+    assert np.array_equal(tiffio.read_page(p), x16)
+
+
+def test_product_never_imports_the_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for d, _, files in os.walk(os.path.join(root, "unmicst_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(d, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f

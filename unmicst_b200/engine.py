@@ -72,6 +72,17 @@ def split_tile_rows(npr: int, parts: int) -> List[Tuple[int, int]]:
     return out
 
 
+def band_rows_py(H: int, S: int, tile_rows: Tuple[int, int]) -> Tuple[int, int]:
+    """Image rows [r0, r1) owned by the tile-row band [a, b) — pure-Python twin of umx_band_rows:
+    the band emits padded-frame rows [a*sub, b*sub) (to the frame end for the last band)."""
+    m, sub, npr, _ = tile_geometry(H, 1, S)
+    a, b = tile_rows
+    b = npr if b <= 0 or b > npr else b
+    p0 = a * sub
+    p1 = npr * sub + 2 * m if b == npr else b * sub
+    return min(H, max(0, p0 - m)), min(H, max(0, p1 - m))
+
+
 class Engine:
     def __init__(self, model: Model, device: int = 0, precision: str = "default", max_batch_tiles: int = 0):
         L = lib()
