@@ -83,12 +83,36 @@ def band_rows_py(H: int, S: int, tile_rows: Tuple[int, int]) -> Tuple[int, int]:
     return min(H, max(0, p0 - m)), min(H, max(0, p1 - m))
 
 
+AUTO_TOLERANCE = 5e-4     # max|dp| of fp16 single-pass vs split3 on the probe tiles (4x under the 2e-3 contract)
+
+
 class Engine:
-    def __init__(self, model: Model, device: int = 0, precision: str = "default", max_batch_tiles: int = 0):
+    """precision: 'default'/'split3' (fp16 hi/lo split, ~fp32 accurate, always within the 2e-3 contract),
+    'single' (one fp16 MMA per product: ~3x less tensor work, accuracy depends on how steep the
+    model's softmax is), 'fp32' (CUDA cores only), or 'auto': build both tensor variants, run probe
+    tiles through them and keep 'single' only if it stays within AUTO_TOLERANCE of 'split3'."""
+
+    def __init__(self, model: Model, device: int = 0, precision: str = "default", max_batch_tiles: int = 0,
+                 probe_tiles: Optional[np.ndarray] = None):
+        self.auto_report = None
+        if precision == "auto":
+            ref = Engine(model, device, "split3", max_batch_tiles)
+            cand = Engine(model, device, "single", max_batch_tiles)
+            if probe_tiles is None:
+                rng = np.random.default_rng(2024)
+                probe_tiles = rng.normal(size=(16, ref.S, ref.S, ref.C)).astype(np.float32)
+            d = float(np.abs(ref.forward_tiles(probe_tiles) - cand.forward_tiles(probe_tiles)).max())
+            keep, drop = (cand, ref) if d <= AUTO_TOLERANCE else (ref, cand)
+            drop.close()
+            self.__dict__.update(keep.__dict__)
+            keep._h = None
+            self.auto_report = {"single_vs_split3_max_abs_dp": d, "tolerance": AUTO_TOLERANCE, "chosen": self.precision}
+            return
         L = lib()
         hp = model.hp
         self.model = model
         self.device = device
+        self.precision = "split3" if precision == "default" else precision
         self.S, self.C, self.K = int(hp["imSize"]), int(hp["nChannels"]), int(hp["nClasses"])
         desc = _lib.umx_model_desc()
         desc.abi_version = _lib.UMX_ABI_VERSION
