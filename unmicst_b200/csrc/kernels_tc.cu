@@ -73,6 +73,43 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
+// ---- CTA-pair (cta_group::2) variants: the MMA spans two SMs (M = 256); each CTA stages its own 128
+// A rows and half of the B rows, all signalling the leader CTA's barriers.
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;     // clears the CTA-rank bit of a shared::cluster address -> even CTA of the pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerMask) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row swizzle atoms 1024 B apart.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
@@ -98,11 +135,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 
 struct TileCoord { int phase, n0, y0, x0, n_idx; };
 
-__device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int tile, int m_tiles) {
+// work item -> (phase, M unit, N tile); an M unit is one M tile, or a pair of M tiles in CTA-pair mode
+__device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int item, int m_units, int per_unit, int rank) {
     TileCoord t;
-    t.n_idx = tile % p.n_ntiles;
-    const int mt = (tile / p.n_ntiles) % m_tiles;
-    t.phase = tile / (p.n_ntiles * m_tiles);
+    t.n_idx = item % p.n_ntiles;
+    const int mt = ((item / p.n_ntiles) % m_units) * per_unit + rank;
+    t.phase = item / (p.n_ntiles * m_units);
     if (p.bn > 1) { t.n0 = mt * p.bn; t.y0 = 0; t.x0 = 0; }
     else {
         const int bx = p.in_w / p.bw, by = p.in_h / p.bh;
@@ -120,14 +158,14 @@ __device__ __forceinline__ float act_fn(float v, int act, float leaky) {
 }
 
 // SKIPC = channels of the narrow fp32 skip source folded into the epilogue (0 = none).
-template <int SKIPC>
+template <int SKIPC, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ TcConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int a_bytes = p.planes * kAPlaneBytes;
-    const int b_plane_bytes = p.n_t * 128;
+    const int b_plane_bytes = (PAIR ? p.n_t / 2 : p.n_t) * 128;     // pair mode: each CTA stages half of the N rows
     const int b_bytes = p.planes * b_plane_bytes;
     const int stage_bytes = a_bytes + b_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
@@ -148,6 +186,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = PAIR ? (int)cluster_ctarank() : 0;
+    const bool leader = rank == 0;
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA0);
         if (p.c1 > 0) tma_prefetch_desc(&mapA1);
@@ -156,28 +196,38 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < p.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-            for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+            for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, PAIR ? 8 : 4); }
             fence_barrier_init();
         }
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();       // peer barriers are initialised before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     const int m_tiles = (p.bn > 1) ? (p.n_tiles + p.bn - 1) / p.bn : p.n_tiles * (p.in_w / p.bw) * (p.in_h / p.bh);
-    const int total = p.nphase * m_tiles * p.n_ntiles;
+    const int per_unit = PAIR ? 2 : 1;
+    const int m_units = (m_tiles + per_unit - 1) / per_unit;
+    const int total = p.nphase * m_units * p.n_ntiles;
+    const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int item_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int nch0 = (p.c0 + 63) >> 6, nch1 = (p.c1 + 63) >> 6;
 
     if (warp == 0) {
         if (lane == 0) {
             // ================= TMA producer =================
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                const TileCoord t = decode_tile(p, tile, m_tiles);
+            for (int tile = item0; tile < total; tile += item_step) {
+                const TileCoord t = decode_tile(p, tile, m_units, per_unit, rank);
                 const int ntap = p.ntaps[t.phase];
                 for (int tp = 0; tp < ntap; ++tp) {
                     const TcTap tap = p.taps[t.phase][tp];
@@ -186,23 +236,31 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         const int cc = (second ? cb - nch0 : cb) * 64;
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
                         const uint32_t fb = full0 + 8 * stage;
-                        mbar_expect_tx(fb, (uint32_t)stage_bytes);
                         const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                        tma_load_5d(sa, second ? &mapA1 : &mapA0, fb, cc, t.x0 + tap.dx, t.y0 + tap.dy, t.n0, 0);
-                        tma_load_4d(sa + a_bytes, &mapB, fb, (second ? p.c0 : 0) + cc, t.n_idx * p.n_t, tap.wi, 0);
+                        if (PAIR) {
+                            // the leader's barrier collects the bytes of both CTAs
+                            if (leader) mbar_expect_tx(fb, 2u * (uint32_t)stage_bytes);
+                            tma_load_5d_pair(sa, second ? &mapA1 : &mapA0, fb, cc, t.x0 + tap.dx, t.y0 + tap.dy, t.n0, 0);
+                            tma_load_4d_pair(sa + a_bytes, &mapB, fb, (second ? p.c0 : 0) + cc,
+                                             t.n_idx * p.n_t + rank * (p.n_t / 2), tap.wi, 0);
+                        } else {
+                            mbar_expect_tx(fb, (uint32_t)stage_bytes);
+                            tma_load_5d(sa, second ? &mapA1 : &mapA0, fb, cc, t.x0 + tap.dx, t.y0 + tap.dy, t.n0, 0);
+                            tma_load_4d(sa + a_bytes, &mapB, fb, (second ? p.c0 : 0) + cc, t.n_idx * p.n_t, tap.wi, 0);
+                        }
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ================= MMA issuer =================
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_t >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        if (lane == 0 && leader) {
+            // ================= MMA issuer (leader CTA only in pair mode) =================
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_t >> 3) << 17) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                const TileCoord t = decode_tile(p, tile, m_tiles);
+            for (int tile = item0; tile < total; tile += item_step) {
+                const TileCoord t = decode_tile(p, tile, m_units, per_unit, rank);
                 const int ntap = p.ntaps[t.phase];
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
@@ -220,20 +278,22 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         const uint32_t sb = sa + a_bytes;
                         for (int k = 0; k < nk; ++k) {
                             const uint64_t ah = umma_desc(sa + k * 32), bh = umma_desc(sb + k * 32);
-                            umma_f16(tmem_d, ah, bh, idesc, accumulate);
+                            if (PAIR) umma_f16_pair(tmem_d, ah, bh, idesc, accumulate); else umma_f16(tmem_d, ah, bh, idesc, accumulate);
                             accumulate = 1;
                             if (p.planes == 2) {
                                 const uint64_t al = umma_desc(sa + kAPlaneBytes + k * 32);
                                 const uint64_t bl = umma_desc(sb + b_plane_bytes + k * 32);
-                                umma_f16(tmem_d, ah, bl, idesc, 1);
-                                umma_f16(tmem_d, al, bh, idesc, 1);
+                                if (PAIR) { umma_f16_pair(tmem_d, ah, bl, idesc, 1); umma_f16_pair(tmem_d, al, bh, idesc, 1); }
+                                else { umma_f16(tmem_d, ah, bl, idesc, 1); umma_f16(tmem_d, al, bh, idesc, 1); }
                             }
                         }
-                        umma_commit(empty0 + 8 * stage);          // frees the smem slot when these MMAs retire
+                        // frees the smem slot (in both CTAs) when these MMAs retire
+                        if (PAIR) umma_commit_pair(empty0 + 8 * stage); else umma_commit(empty0 + 8 * stage);
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                 }
-                umma_commit(tfull0 + 8 * acc);                    // accumulator ready for the epilogue
+                // accumulator ready for the epilogue (of both CTAs)
+                if (PAIR) umma_commit_pair(tfull0 + 8 * acc); else umma_commit(tfull0 + 8 * acc);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -243,8 +303,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int m = q * 32 + lane;
         const int xl = m % p.bw, yl = (m / p.bw) % p.bh, nl = m / (p.bw * p.bh);
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-            const TileCoord t = decode_tile(p, tile, m_tiles);
+        for (int tile = item0; tile < total; tile += item_step) {
+            const TileCoord t = decode_tile(p, tile, m_units, per_unit, rank);
             const int n = t.n0 + nl, y = t.y0 + yl, x = t.x0 + xl;
             const bool valid = n < p.n_tiles;
             int oh, ow, oy, ox; bool writer = valid;
@@ -352,16 +412,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+            if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty0 + 8 * acc); else mbar_arrive(tempty0 + 8 * acc); }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();       // the peer may still be reading this CTA's smem / arriving on its barriers
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -383,34 +445,61 @@ EncodeTiledFn encode_fn() {
 }  // namespace
 
 size_t tc_conv_smem_bytes(const TcConvParams& p) {
-    const size_t stage = (size_t)p.planes * (kAPlaneBytes + (size_t)p.n_t * 128);
+    const size_t stage = (size_t)p.planes * (kAPlaneBytes + (size_t)(p.pair ? p.n_t / 2 : p.n_t) * 128);
     const size_t tables = ((size_t)9 * p.skip_c * p.cout + (p.top_w ? (size_t)p.cout * p.top_k + 4 : 0)) * sizeof(float);
     return (size_t)p.stages * stage + (2 * p.stages + 4) * 8 + 16 + tables + 1024;
 }
 
+template <int SKIPC, bool PAIR>
+static cudaError_t configure_one() {
+    return cudaFuncSetAttribute(tc_conv_kernel<SKIPC, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
 cudaError_t tc_conv_configure() {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = configure_one<0, false>();
+    if (e == cudaSuccess) e = configure_one<1, false>();
+    if (e == cudaSuccess) e = configure_one<2, false>();
+    if (e == cudaSuccess) e = configure_one<0, true>();
+    if (e == cudaSuccess) e = configure_one<1, true>();
+    if (e == cudaSuccess) e = configure_one<2, true>();
     return e;
+}
+
+template <int SKIPC, bool PAIR>
+static cudaError_t launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcConvParams& p,
+                              int grid, size_t smem, cudaStream_t s) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, tc_conv_kernel<SKIPC, PAIR>, a0, a1, b, p);
 }
 
 cudaError_t launch_tc_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcConvParams& p,
                            int num_sms, cudaStream_t s) {
     const int m_tiles = (p.bn > 1) ? (p.n_tiles + p.bn - 1) / p.bn : p.n_tiles * (p.in_w / p.bw) * (p.in_h / p.bh);
-    const int total = p.nphase * m_tiles * p.n_ntiles;
+    const int per_unit = p.pair ? 2 : 1;
+    const int total = p.nphase * ((m_tiles + per_unit - 1) / per_unit) * p.n_ntiles;
     if (total == 0) return cudaSuccess;
-    const int grid = total < num_sms ? total : num_sms;
+    int grid = total * per_unit < num_sms ? total * per_unit : num_sms;
+    if (p.pair) grid &= ~1;
     // at least ~120 KB so that exactly one CTA (and its 512 TMEM columns) lives on an SM
     size_t smem = tc_conv_smem_bytes(p);
     if (smem < 120 * 1024) smem = 120 * 1024;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     const int skipc = p.skip_src ? p.skip_c : 0;
-    if (skipc == 0) tc_conv_kernel<0><<<grid, kThreads, smem, s>>>(a0, a1, b, p);
-    else if (skipc == 1) tc_conv_kernel<1><<<grid, kThreads, smem, s>>>(a0, a1, b, p);
-    else if (skipc == 2) tc_conv_kernel<2><<<grid, kThreads, smem, s>>>(a0, a1, b, p);
-    else return cudaErrorInvalidValue;
-    return cudaGetLastError();
+    if (p.pair) {
+        if (skipc == 0) return launch_one<0, true>(a0, a1, b, p, grid, smem, s);
+        if (skipc == 1) return launch_one<1, true>(a0, a1, b, p, grid, smem, s);
+        if (skipc == 2) return launch_one<2, true>(a0, a1, b, p, grid, smem, s);
+    } else {
+        if (skipc == 0) return launch_one<0, false>(a0, a1, b, p, grid, smem, s);
+        if (skipc == 1) return launch_one<1, false>(a0, a1, b, p, grid, smem, s);
+        if (skipc == 2) return launch_one<2, false>(a0, a1, b, p, grid, smem, s);
+    }
+    return cudaErrorInvalidValue;
 }
 
 int make_act_tensor_map(CUtensorMap* out, const __half* base, int planes, int64_t plane_elems, int n, int h, int w, int c,

@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -434,7 +435,11 @@ int lower_conv_tc(umx_handle* h, Op& op) {
         for (int i = 0; i < tt.ntaps[ph]; ++i) tp.taps[ph][i] = TcTap{tt.dy[ph][i], tt.dx[ph][i], tt.wi[ph][i], 0};
     }
     tp.planes = planes;
-    const size_t stage = (size_t)planes * (16384 + (size_t)tp.n_t * 128);
+    {
+        const char* e = getenv("UMX_TC_PAIR");
+        tp.pair = (e ? atoi(e) : 1) && (tp.n_t % 32 == 0 || tp.n_t % 16 == 0) && ((tp.n_t / 2) % 8 == 0) ? 1 : 0;
+    }
+    const size_t stage = (size_t)planes * (16384 + (size_t)(tp.pair ? tp.n_t / 2 : tp.n_t) * 128);
     tp.stages = (int)std::min<size_t>(6, (227 * 1024 - 2048) / stage);
     if (tp.stages < 2) { set_error("%s: pipeline does not fit shared memory", op.name.c_str()); return UMX_EINVAL; }
     tp.act = sp.act; tp.leaky = kLeaky; tp.pool = sp.pool ? 1 : 0;
@@ -473,7 +478,7 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     UMX_CUDA_TRY(cudaMalloc(&dw, wh.size() * sizeof(__half)));
     h->dev_allocs.push_back(reinterpret_cast<float*>(dw));
     UMX_CUDA_TRY(cudaMemcpy(dw, wh.data(), wh.size() * sizeof(__half), cudaMemcpyHostToDevice));
-    int rc = make_weight_tensor_map(&op.mapB, dw, planes, 9, sp.cout, cin, tp.n_t, planes);
+    int rc = make_weight_tensor_map(&op.mapB, dw, planes, 9, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, planes);
     if (rc) { set_error("%s: cuTensorMapEncodeTiled(weights) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
     if (!a0.dh || (a1 && !a1->dh)) { set_error("%s: fp16 source buffer missing", op.name.c_str()); return UMX_EINVAL; }
     rc = make_act_tensor_map(&op.mapA0, a0.dh, a0.planes, a0.plane_elems, h->cap_tiles, a0.h, a0.w, a0.c, tp.bw, tp.bh, tp.bn, planes);
