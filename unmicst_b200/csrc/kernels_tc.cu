@@ -237,16 +237,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
                         const uint32_t fb = full0 + 8 * stage;
                         const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                        const bool doA = !(p.exp_flags & 1), doB = !(p.exp_flags & 2);
+                        const uint32_t tx = (doA ? a_bytes : 0) + (doB ? b_bytes : 0);
                         if (PAIR) {
                             // the leader's barrier collects the bytes of both CTAs
-                            if (leader) mbar_expect_tx(fb, 2u * (uint32_t)stage_bytes);
-                            tma_load_5d_pair(sa, second ? &mapA1 : &mapA0, fb, cc, t.x0 + tap.dx, t.y0 + tap.dy, t.n0, 0);
-                            tma_load_4d_pair(sa + a_bytes, &mapB, fb, (second ? p.c0 : 0) + cc,
-                                             t.n_idx * p.n_t + rank * (p.n_t / 2), tap.wi, 0);
+                            if (leader) mbar_expect_tx(fb, 2u * tx);
+                            if (doA) tma_load_5d_pair(sa, second ? &mapA1 : &mapA0, fb, cc, t.x0 + tap.dx, t.y0 + tap.dy, t.n0, 0);
+                            if (doB) tma_load_4d_pair(sa + a_bytes, &mapB, fb, (second ? p.c0 : 0) + cc,
+                                                      t.n_idx * p.n_t + rank * (p.n_t / 2), tap.wi, 0);
                         } else {
-                            mbar_expect_tx(fb, (uint32_t)stage_bytes);
-                            tma_load_5d(sa, second ? &mapA1 : &mapA0, fb, cc, t.x0 + tap.dx, t.y0 + tap.dy, t.n0, 0);
-                            tma_load_4d(sa + a_bytes, &mapB, fb, (second ? p.c0 : 0) + cc, t.n_idx * p.n_t, tap.wi, 0);
+                            mbar_expect_tx(fb, tx);
+                            if (doA) tma_load_5d(sa, second ? &mapA1 : &mapA0, fb, cc, t.x0 + tap.dx, t.y0 + tap.dy, t.n0, 0);
+                            if (doB) tma_load_4d(sa + a_bytes, &mapB, fb, (second ? p.c0 : 0) + cc, t.n_idx * p.n_t, tap.wi, 0);
                         }
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
@@ -271,7 +273,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         const bool second = cb >= nch0;
                         const int cc = (second ? cb - nch0 : cb) * 64;
                         const int kvalid = min(64, (second ? p.c1 : p.c0) - cc);
-                        const int nk = (kvalid + 15) >> 4;
+                        const int nk = (p.exp_flags & 4) ? 1 : (kvalid + 15) >> 4;
                         mbar_wait(full0 + 8 * stage, phase);
                         tc_fence_after();
                         const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
@@ -329,7 +331,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
-            for (int c16 = 0; c16 < (p.n_t >> 4); ++c16) {
+            for (int c16 = 0; c16 < ((p.exp_flags & 8) ? 1 : (p.n_t >> 4)); ++c16) {
                 uint32_t r[16];
                 tmem_ld16(tbase + c16 * 16, r);
                 const int co = t.n_idx * p.n_t + c16 * 16;

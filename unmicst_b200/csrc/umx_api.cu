@@ -441,6 +441,8 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     }
     const size_t stage = (size_t)planes * (16384 + (size_t)(tp.pair ? tp.n_t / 2 : tp.n_t) * 128);
     tp.stages = (int)std::min<size_t>(6, (227 * 1024 - 2048) / stage);
+    if (const char* e = getenv("UMX_TC_EXP")) tp.exp_flags = atoi(e);
+    if (const char* e = getenv("UMX_TC_STAGES")) tp.stages = std::max(2, std::min(tp.stages, atoi(e)));
     if (tp.stages < 2) { set_error("%s: pipeline does not fit shared memory", op.name.c_str()); return UMX_EINVAL; }
     tp.act = sp.act; tp.leaky = kLeaky; tp.pool = sp.pool ? 1 : 0;
     float* d = nullptr;

@@ -22,6 +22,7 @@ struct TcConvParams {
     TcTap   taps[4][9];
     int32_t planes;              // 1: fp16 operands, 1 MMA/product; 2: hi/lo split, 3 MMAs/product
     int32_t stages;              // smem pipeline depth
+    int32_t exp_flags;           // timing experiments only (results invalid): 1 no A loads, 2 no B loads, 4 one MMA per stage, 8 no epilogue math
     int32_t pair;                // 1: CTA pairs, tcgen05.mma.cta_group::2 (M = 256 across two SMs)
     int32_t act;                 // umx::Act
     float   leaky;
