@@ -147,6 +147,7 @@ def cpu_baseline(model, image, budget_s: float = 15.0):
     of the same image sized to ~budget_s seconds.  Returns MP/s of valid output pixels."""
     import torch
     from oracle import pi2d_oracle
+    torch.set_num_threads(os.cpu_count() or 1)       # torchrun pins OMP_NUM_THREADS=1; the baseline gets every host core
     S, C, B = model.hp["imSize"], model.hp["nChannels"], model.hp["batchSize"]
     sub = S - 2 * (S // 8)
     fw = oracle_forward(model)
