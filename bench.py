@@ -242,7 +242,10 @@ def run_ours(args):
     img = make_image(args.workload, H, W)
     premap = None
     from unmicst_b200.engine import PreMap
-    premap = PreMap(in_scale=1.0 / 65535)        # solo feeds img_as_float(u16) un-stretched (UnMicst1-5.py:816)
+    if model_name == "nucleiDAPI1-5":
+        premap = PreMap(in_scale=1.0 / 65535)    # solo feeds img_as_float(u16) un-stretched (UnMicst1-5.py:816)
+    else:                                        # the other tools stretch to (0, 0.983) (UnMicst.py:627-631)
+        premap = PreMap(in_scale=1.0 / 65535, rescale=True, imin=float(img.min()) / 65535, imax=float(img.max()) / 65535)
 
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)

@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(NTHR) conv_simt_kernel(const __grid_constant__
                 else
                     for (int j = 0; j < 4; ++j) if (co + j < p.cout) o[j] = v[j];
             }
-            if (p.out_h) store_h2x4(p.out_h + oo, p.out_plane_elems, p.out_planes, v);
+            if (p.out_h) store_h2x4(p.out_h + (((int64_t)gn * oh + oy) * ow + ox) * p.out_cs + co, p.out_plane_elems, p.out_planes, v);
         }
     } else {
         const int oh = p.in_h * p.os, ow = p.in_w * p.os;
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(NTHR) conv_simt_kernel(const __grid_constant__
                 else
                     for (int j = 0; j < 4; ++j) if (co + j < p.cout) o[j] = acc[pp][j];
             }
-            if (p.out_h) store_h2x4(p.out_h + oo, p.out_plane_elems, p.out_planes, acc[pp]);
+            if (p.out_h) store_h2x4(p.out_h + (((int64_t)gn * oh + oy) * ow + ox) * p.out_cs + co, p.out_plane_elems, p.out_planes, acc[pp]);
         }
     }
 }

@@ -175,13 +175,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const uint32_t tempty0 = tfull0 + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
     // small fp32 tables for the epilogue: skip-term weights [9][SKIPC][cout], lt weights [cout][K], lt bias [K]
+    // (rows padded with zeros to cpad = n_ntiles * n_t columns so the epilogue needs no channel guards)
+    const int cpad = p.n_ntiles * p.n_t;
     float* s_skipw = reinterpret_cast<float*>(tmem_slot + 4);
-    float* s_topw = s_skipw + 9 * SKIPC * p.cout;
-    float* s_topb = s_topw + (p.top_w ? p.cout * p.top_k : 0);
+    float* s_topw = s_skipw + 9 * SKIPC * cpad;
+    float* s_topb = s_topw + (p.top_w ? cpad * p.top_k : 0);
     if (SKIPC > 0)
-        for (int i = threadIdx.x; i < 9 * SKIPC * p.cout; i += kThreads) s_skipw[i] = p.skip_w[i];
+        for (int i = threadIdx.x; i < 9 * SKIPC * cpad; i += kThreads) {
+            const int c = i % cpad;
+            s_skipw[i] = c < p.cout ? p.skip_w[(i / cpad) * p.cout + c] : 0.f;
+        }
     if (p.top_w) {
-        for (int i = threadIdx.x; i < p.cout * p.top_k; i += kThreads) s_topw[i] = p.top_w[i];
+        for (int i = threadIdx.x; i < cpad * p.top_k; i += kThreads) s_topw[i] = (i / p.top_k) < p.cout ? p.top_w[i] : 0.f;
         if (threadIdx.x < p.top_k) s_topb[threadIdx.x] = p.top_b ? p.top_b[threadIdx.x] : 0.f;
     }
 
@@ -342,14 +347,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     if (p.bias && co + j < p.cout) b = __ldg(p.bias + co + j);
                     v[j] = __uint_as_float(r[j]) + b;
                 }
-                if (SKIPC > 0 && co + 16 <= p.cout) {
+                if (SKIPC > 0) {
 #pragma unroll
                     for (int tp = 0; tp < 9; ++tp) {
                         const int wi = p.taps[0][tp].wi;
 #pragma unroll
                         for (int cs = 0; cs < SKIPC; ++cs) {
                             const float xv = xs[tp * SKIPC + cs];
-                            const float4* w4 = reinterpret_cast<const float4*>(s_skipw + (wi * SKIPC + cs) * p.cout + co);
+                            const float4* w4 = reinterpret_cast<const float4*>(s_skipw + (wi * SKIPC + cs) * cpad + co);
 #pragma unroll
                             for (int j4 = 0; j4 < 4; ++j4) {
                                 const float4 w = w4[j4];
@@ -361,7 +366,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = act_fn(v[j], p.act, p.leaky);
-                if (p.top_w && co + 16 <= p.cout) {
+                if (p.top_w) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const float* wk = s_topw + (co + j) * p.top_k;
@@ -380,13 +385,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
                 for (int h8 = 0; h8 < 2; ++h8) {
                     const int c = co + h8 * 8;
-                    if (!writer || c >= p.cout) continue;
-                    if (p.out_f) {
-                        float4* o = reinterpret_cast<float4*>(p.out_f + opix * p.cout + c);
-                        o[0] = make_float4(v[h8 * 8 + 0], v[h8 * 8 + 1], v[h8 * 8 + 2], v[h8 * 8 + 3]);
-                        o[1] = make_float4(v[h8 * 8 + 4], v[h8 * 8 + 5], v[h8 * 8 + 6], v[h8 * 8 + 7]);
+                    if (!writer) continue;
+                    if (p.out_f && c < p.cout) {
+                        float* of = p.out_f + opix * p.cout + c;
+                        if (c + 8 <= p.cout && !(p.cout & 3)) {
+                            reinterpret_cast<float4*>(of)[0] = make_float4(v[h8 * 8 + 0], v[h8 * 8 + 1], v[h8 * 8 + 2], v[h8 * 8 + 3]);
+                            reinterpret_cast<float4*>(of)[1] = make_float4(v[h8 * 8 + 4], v[h8 * 8 + 5], v[h8 * 8 + 6], v[h8 * 8 + 7]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) if (c + j < p.cout) of[j] = v[h8 * 8 + j];
+                        }
                     }
-                    if (p.out_h) {
+                    if (p.out_h && c < p.out_cs) {       // storage channels are padded to a multiple of 8; pad lanes hold 0
                         __half2 hi[4], lo[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -395,7 +405,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             hi[j] = __halves2half2(ha, hb);
                             lo[j] = __halves2half2(__float2half_rn(a - __half2float(ha)), __float2half_rn(b - __half2float(hb)));
                         }
-                        __half* o = p.out_h + opix * p.cout + c;
+                        __half* o = p.out_h + opix * p.out_cs + c;
                         *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(hi);
                         if (p.out_planes == 2) *reinterpret_cast<uint4*>(o + p.out_plane_elems) = *reinterpret_cast<uint4*>(lo);
                     }
@@ -448,7 +458,8 @@ EncodeTiledFn encode_fn() {
 
 size_t tc_conv_smem_bytes(const TcConvParams& p) {
     const size_t stage = (size_t)p.planes * (kAPlaneBytes + (size_t)(p.pair ? p.n_t / 2 : p.n_t) * 128);
-    const size_t tables = ((size_t)9 * p.skip_c * p.cout + (p.top_w ? (size_t)p.cout * p.top_k + 4 : 0)) * sizeof(float);
+    const size_t cpad = (size_t)p.n_ntiles * p.n_t;
+    const size_t tables = ((size_t)9 * p.skip_c * cpad + (p.top_w ? cpad * p.top_k + 4 : 0)) * sizeof(float);
     return (size_t)p.stages * stage + (2 * p.stages + 4) * 8 + 16 + tables + 1024;
 }
 

@@ -321,7 +321,7 @@ bool tc_skip_mode(const umx_handle* h, const Op& op) {
     if (sp.terms.size() != 1 || sp.terms[0].src1 < 0 || sp.transpose || sp.pool) return false;
     const Buffer& a = h->bufs[sp.terms[0].src0];
     const Buffer& b = h->bufs[sp.terms[0].src1];
-    return a.c <= 2 && b.c % 8 == 0 && sp.cout % 16 == 0;
+    return a.c <= 2 && b.c >= 8;
 }
 
 bool tc_eligible(const umx_handle* h, const Op& op) {
@@ -329,11 +329,9 @@ bool tc_eligible(const umx_handle* h, const Op& op) {
     const ConvSpec& sp = op.spec;
     if (sp.terms.size() != 1 || sp.has_post || sp.terms[0].k != 3) return false;
     const Buffer& a = h->bufs[sp.terms[0].src0];
-    if (sp.cout % 8 != 0 || a.h < 4 || a.w < 4) return false;
+    if (a.h < 4 || a.w < 4) return false;
     if (tc_skip_mode(h, op)) return true;
-    if (a.c % 8 != 0) return false;
-    if (sp.terms[0].src1 >= 0 && h->bufs[sp.terms[0].src1].c % 8 != 0) return false;
-    return true;
+    return a.c >= 8;        // narrower inputs (the raw image) stay on the CUDA cores
 }
 
 int pick_n_tile(int cout) {
@@ -387,7 +385,7 @@ int lower_conv_simt(umx_handle* h, Op& op) {
     }
     const Buffer& ob = h->bufs[op.out_buf];
     cp.out = ob.d; cp.out_h = ob.dh; cp.out_planes = ob.planes; cp.out_plane_elems = ob.plane_elems;
-    if (cp.out_h && (sp.cout & 3)) { set_error("%s: fp16 output needs cout %% 4 == 0", op.name.c_str()); return UMX_EINVAL; }
+    cp.out_cs = ob.cs();
     if (conv_simt_smem_bytes(cp) > 100 * 1024) { set_error("%s: shared-memory tile too large", op.name.c_str()); return UMX_EINVAL; }
     return UMX_OK;
 }
@@ -425,7 +423,7 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     const int planes = h->precision == UMX_PREC_SINGLE ? 1 : 2;
     tp.in_h = a0.h; tp.in_w = a0.w;
     tp.bw = std::min(a0.w, 16); tp.bh = std::min(a0.h, 128 / tp.bw); tp.bn = 128 / (tp.bw * tp.bh);
-    tp.c0 = a0.c; tp.c1 = a1 ? a1->c : 0;
+    tp.c0 = a0.cs(); tp.c1 = a1 ? a1->cs() : 0;          // storage channels (zero-padded to a multiple of 8)
     tp.cout = sp.cout; tp.n_t = pick_n_tile(sp.cout); tp.n_ntiles = (sp.cout + tp.n_t - 1) / tp.n_t;
     tp.nphase = sp.transpose ? 4 : 1; tp.os = sp.transpose ? 2 : 1;
     ConvTerm tt; memset(&tt, 0, sizeof(tt));
@@ -448,13 +446,22 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     float* d = nullptr;
     if (sp.has_bias) { UMX_TRY(upload(h, sp.bias, &d)); tp.bias = d; }
     const Buffer& ob = h->bufs[op.out_buf];
-    tp.out_f = ob.d; tp.out_h = ob.dh; tp.out_planes = ob.planes; tp.out_plane_elems = ob.plane_elems;
-    // weights -> fp16 planes on the device
+    tp.out_f = ob.d; tp.out_h = ob.dh; tp.out_planes = ob.planes; tp.out_plane_elems = ob.plane_elems; tp.out_cs = ob.cs();
+    // weights -> fp16 planes on the device; input-channel rows follow the padded storage layout [c0s | c1s]
     const int cin = tp.c0 + tp.c1;
-    std::vector<float> wmain = T.w;
+    std::vector<float> wmain;
+    if (!op.skip_mode) {
+        const int r0 = a0.c, r1 = a1 ? a1->c : 0;
+        wmain.assign((size_t)9 * cin * sp.cout, 0.f);
+        for (int t = 0; t < 9; ++t)
+            for (int i = 0; i < r0 + r1; ++i) {
+                const int dst = i < r0 ? i : tp.c0 + (i - r0);
+                memcpy(&wmain[((size_t)t * cin + dst) * sp.cout], &T.w[((size_t)t * (r0 + r1) + i) * sp.cout], sp.cout * sizeof(float));
+            }
+    }
     if (op.skip_mode) {
         const Buffer& sk = h->bufs[T.src0];
-        const int cs = sk.c, ctot = cs + cin;
+        const int cs = sk.c, ctot = cs + a0.c;
         std::vector<float> wskip((size_t)9 * cs * sp.cout);
         wmain.assign((size_t)9 * cin * sp.cout, 0.f);
         for (int t = 0; t < 9; ++t)
@@ -483,10 +490,10 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     int rc = make_weight_tensor_map(&op.mapB, dw, planes, 9, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, planes);
     if (rc) { set_error("%s: cuTensorMapEncodeTiled(weights) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
     if (!a0.dh || (a1 && !a1->dh)) { set_error("%s: fp16 source buffer missing", op.name.c_str()); return UMX_EINVAL; }
-    rc = make_act_tensor_map(&op.mapA0, a0.dh, a0.planes, a0.plane_elems, h->cap_tiles, a0.h, a0.w, a0.c, tp.bw, tp.bh, tp.bn, planes);
+    rc = make_act_tensor_map(&op.mapA0, a0.dh, a0.planes, a0.plane_elems, h->cap_tiles, a0.h, a0.w, a0.cs(), tp.bw, tp.bh, tp.bn, planes);
     if (rc) { set_error("%s: cuTensorMapEncodeTiled(A0) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
     if (a1) {
-        rc = make_act_tensor_map(&op.mapA1, a1->dh, a1->planes, a1->plane_elems, h->cap_tiles, a1->h, a1->w, a1->c, tp.bw, tp.bh, tp.bn, planes);
+        rc = make_act_tensor_map(&op.mapA1, a1->dh, a1->planes, a1->plane_elems, h->cap_tiles, a1->h, a1->w, a1->cs(), tp.bw, tp.bh, tp.bn, planes);
         if (rc) { set_error("%s: cuTensorMapEncodeTiled(A1) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
     } else {
         op.mapA1 = op.mapA0;
@@ -508,7 +515,7 @@ int lower_plan(umx_handle* h) {
         Op& top = h->ops[i];
         Op& prev = h->ops[i - 1];
         if (top.kind == OP_TOP && prev.kind == OP_CONV && prev.use_tc && prev.out_buf == top.top_src &&
-            prev.spec.cout % 16 == 0 && pick_n_tile(prev.spec.cout) == prev.spec.cout && !prev.spec.pool && !prev.spec.transpose) {
+            pick_n_tile(prev.spec.cout) >= prev.spec.cout && !prev.spec.pool && !prev.spec.transpose) {
             prev.fuse_top = (int)i;
             top.fused_away = true;
             const Buffer& ob = h->bufs[prev.out_buf];
@@ -535,7 +542,7 @@ int lower_plan(umx_handle* h) {
     for (auto& b : h->bufs) {
         if (b.need_f) UMX_CUDA_TRY(cudaMalloc(&b.d, (size_t)h->cap_tiles * b.per_tile() * sizeof(float)));
         if (b.need_h) {
-            b.planes = planes; b.plane_elems = (int64_t)h->cap_tiles * b.per_tile();
+            b.planes = planes; b.plane_elems = (int64_t)h->cap_tiles * b.per_tile_h();
             UMX_CUDA_TRY(cudaMalloc(&b.dh, (size_t)planes * b.plane_elems * sizeof(__half)));
             UMX_CUDA_TRY(cudaMemset(b.dh, 0, (size_t)planes * b.plane_elems * sizeof(__half)));
         }
@@ -827,10 +834,12 @@ int64_t umx_debug_buffer(umx_handle* h, const char* name, int32_t n_tiles, float
         if (b.d) {
             UMX_CUDA_TRY(cudaMemcpy(out, b.d, n * sizeof(float), cudaMemcpyDeviceToHost));
         } else if (b.dh) {
-            std::vector<__half> tmp(n);
+            const int64_t npix = n / b.c, cs = b.cs();
+            std::vector<__half> tmp(npix * cs);
             for (int pl = 0; pl < b.planes; ++pl) {
-                UMX_CUDA_TRY(cudaMemcpy(tmp.data(), b.dh + pl * b.plane_elems, n * sizeof(__half), cudaMemcpyDeviceToHost));
-                for (int64_t i = 0; i < n; ++i) out[i] = (pl ? out[i] : 0.f) + __half2float(tmp[i]);
+                UMX_CUDA_TRY(cudaMemcpy(tmp.data(), b.dh + pl * b.plane_elems, tmp.size() * sizeof(__half), cudaMemcpyDeviceToHost));
+                for (int64_t px = 0; px < npix; ++px)
+                    for (int c = 0; c < b.c; ++c) out[px * b.c + c] = (pl ? out[px * b.c + c] : 0.f) + __half2float(tmp[px * cs + c]);
             }
         } else { set_error("buffer '%s' is not materialised", name); return UMX_EINVAL; }
         return b.per_tile();

@@ -46,7 +46,9 @@ struct Buffer {
     __half* dh = nullptr;           // [planes][cap][h][w][c] fp16
     int planes = 0;
     int64_t plane_elems = 0;
+    int cs() const { return (c + 7) & ~7; }          // channel stride of the fp16 planes (TMA needs 16-byte strides)
     int64_t per_tile() const { return (int64_t)h * w * c; }
+    int64_t per_tile_h() const { return (int64_t)h * w * cs(); }
 };
 
 struct TermHost {

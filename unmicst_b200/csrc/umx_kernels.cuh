@@ -47,6 +47,7 @@ struct ConvParams {
     __half* out_h;              // fp16 hi[/lo] planes [out_planes][n][oh][ow][cout] for tensor-path consumers, or nullptr
     int64_t out_plane_elems;
     int32_t out_planes;
+    int32_t out_cs;             // channel stride of out_h (cout rounded up to 8)
 };
 
 // First layer of the v2 graphs: 3x3 SAME conv from 1 or 2 input channels + bias + activation +

@@ -31,6 +31,7 @@ struct TcConvParams {
     __half* out_h;               // fp16 plane(s) [planes][n][oh][ow][cout] or nullptr
     int64_t out_plane_elems;     // elements between the hi and lo plane
     int32_t out_planes;          // planes to write into out_h (1 or 2)
+    int32_t out_cs;              // channel stride of out_h (cout rounded up to 8; pad channels are written as 0)
     float*  out_f;               // fp32 [n][oh][ow][cout] or nullptr
     // narrow skip source handled in fp32 in the epilogue (raw input channels of lu0.conv2)
     const float* skip_src;       // [n][in_h][in_w][skip_c] or nullptr
