@@ -115,12 +115,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-// A operand with a caller-chosen stride between 8-row groups (halo patches) and optional base-offset field
-__device__ __forceinline__ uint64_t umma_desc_a(uint32_t saddr, uint32_t sbo, int mode) {
-    uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo >> 4) << 32) |
-                 ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-    if (mode == 1) d |= (uint64_t)((saddr >> 7) & 7) << 49;
-    return d;
+__device__ __forceinline__ uint64_t umma_desc_sbo(uint32_t saddr, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -165,29 +162,35 @@ __device__ __forceinline__ float act_fn(float v, int act, float leaky) {
 }
 
 // SKIPC = channels of the narrow fp32 skip source folded into the epilogue (0 = none).
-template <int SKIPC, bool PAIR>
+template <int SKIPC, bool PAIR, bool HALO>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ TcConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    // Two rings: A stages (one 64-channel slab of activations: a per-tap 128-pixel tile, or in halo mode the
-    // whole (bh+halo) x (bw+halo) pixel patch that serves every tap) and B stages (one weight tile per tap/slab).
-    const int a_box_bytes = p.halo ? p.ph * p.pw * 128 : kAPlaneBytes;            // bytes one TMA box delivers per plane
-    const int a_plane_bytes = (a_box_bytes + 1023) & ~1023;                       // plane slots stay 1024-byte aligned
-    const int a_bytes = p.planes * a_plane_bytes;
-    const int b_plane_bytes = (PAIR ? p.n_t / 2 : p.n_t) * 128;                   // pair mode: each CTA stages half of the N rows
-    const int b_bytes = p.planes * b_plane_bytes;
-    uint8_t* smem_b = smem + (size_t)p.a_stages * a_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.b_stages * b_bytes);
-    const uint32_t fullA0 = smem_u32(bars);
-    const uint32_t emptyA0 = fullA0 + 8 * p.a_stages;
-    const uint32_t fullB0 = emptyA0 + 8 * p.a_stages;
-    const uint32_t emptyB0 = fullB0 + 8 * p.b_stages;
-    const uint32_t tfull0 = emptyB0 + 8 * p.b_stages;
+    // Plain mode: one ring of `stages` slots, each [A tile planes][B tile planes] for one (tap, 64-channel slab).
+    // Halo mode (high-resolution layers): ring A holds one (bh+halo) x (bw+halo) pixel patch per slab that serves
+    // every tap (A is fetched from L2 once instead of once per tap); ring B holds the weights of `gb` taps per slot.
+    const int planes = p.planes;
+    const int a_box_bytes = HALO ? p.ph * p.pw * 128 : kAPlaneBytes;           // bytes one TMA box delivers per plane
+    const int a_plane_bytes = HALO ? ((a_box_bytes + 1023) & ~1023) : kAPlaneBytes;
+    const int a_bytes = planes * a_plane_bytes;
+    const int b_plane_bytes = (PAIR ? p.n_t / 2 : p.n_t) * 128;     // pair mode: each CTA stages half of the N rows
+    const int b_bytes = planes * b_plane_bytes;
+    const int stage_bytes = HALO ? a_bytes : a_bytes + b_bytes;
+    const int n_stages = p.stages;                                   // plain: ring slots; halo: patch slots
+    const int nb_stages = HALO ? p.b_stages : 0;
+    const int gb = HALO ? p.gb : 1;
+    uint8_t* smem_b = smem + (size_t)n_stages * stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)nb_stages * gb * b_bytes);
+    const uint32_t full0 = smem_u32(bars);
+    const uint32_t empty0 = full0 + 8 * n_stages;
+    const uint32_t fullB0 = empty0 + 8 * n_stages;
+    const uint32_t emptyB0 = fullB0 + 8 * nb_stages;
+    const uint32_t tfull0 = emptyB0 + 8 * nb_stages;
     const uint32_t tempty0 = tfull0 + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.a_stages + 2 * p.b_stages + 4);
-    // small fp32 tables for the epilogue: skip-term weights [9][SKIPC][cpad], lt weights [cpad][K], lt bias [K]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * n_stages + 2 * nb_stages + 4);
+    // small fp32 tables for the epilogue: skip-term weights [9][SKIPC][cout], lt weights [cout][K], lt bias [K]
     // (rows padded with zeros to cpad = n_ntiles * n_t columns so the epilogue needs no channel guards)
     const int cpad = p.n_ntiles * p.n_t;
     float* s_skipw = reinterpret_cast<float*>(tmem_slot + 4);
@@ -213,8 +216,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < p.a_stages; ++s) { mbar_init(fullA0 + 8 * s, 1); mbar_init(emptyA0 + 8 * s, 1); }
-            for (int s = 0; s < p.b_stages; ++s) { mbar_init(fullB0 + 8 * s, 1); mbar_init(emptyB0 + 8 * s, 1); }
+            for (int s = 0; s < n_stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+            for (int s = 0; s < nb_stages; ++s) { mbar_init(fullB0 + 8 * s, 1); mbar_init(emptyB0 + 8 * s, 1); }
             for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, PAIR ? 8 : 4); }
             fence_barrier_init();
         }
@@ -240,108 +243,170 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int item_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int nch0 = (p.c0 + 63) >> 6, nch1 = (p.c1 + 63) >> 6;
-    const int n_chunks = nch0 + nch1;
-    const uint32_t txmul = PAIR ? 2u : 1u;     // the leader's barrier collects the bytes of both CTAs
 
     if (warp == 0) {
         if (lane == 0) {
             // ================= TMA producer =================
-            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            if constexpr (HALO) {
+                const int hx0 = p.hx0, hy0 = p.hy0, n_chunks = nch0 + nch1, c0s = p.c0, n_t = p.n_t;
+                const uint32_t txA = (PAIR ? 2u : 1u) * (uint32_t)(planes * a_box_bytes);
+                int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+                for (int tile = item0; tile < total; tile += item_step) {
+                    const TileCoord t = decode_tile(p, tile, m_units, per_unit, rank);
+                    const int ntap = p.ntaps[t.phase];
+                    const int ncol = t.n_idx * n_t + (PAIR ? rank * (n_t / 2) : 0);
+                    for (int cb = 0; cb < n_chunks; ++cb) {
+                        const bool second = cb >= nch0;
+                        const int cc = (second ? cb - nch0 : cb) * 64;
+                        const CUtensorMap* mapA = second ? &mapA1 : &mapA0;
+                        mbar_wait(empty0 + 8 * sa, pa ^ 1);
+                        const uint32_t fa = full0 + 8 * sa;
+                        const uint32_t da = smem_u32(smem + (size_t)sa * stage_bytes);
+                        if (leader) mbar_expect_tx(fa, txA);
+                        for (int pl = 0; pl < planes; ++pl) {
+                            if (PAIR) tma_load_5d_pair(da + pl * a_plane_bytes, mapA, fa, cc, t.x0 - hx0, t.y0 - hy0, t.n0, pl);
+                            else tma_load_5d(da + pl * a_plane_bytes, mapA, fa, cc, t.x0 - hx0, t.y0 - hy0, t.n0, pl);
+                        }
+                        if (++sa == n_stages) { sa = 0; pa ^= 1; }
+                        for (int t0 = 0; t0 < ntap; t0 += gb) {
+                            const int ng = min(gb, ntap - t0);
+                            mbar_wait(emptyB0 + 8 * sb, pb ^ 1);
+                            const uint32_t fb = fullB0 + 8 * sb;
+                            const uint32_t db = smem_u32(smem_b + (size_t)sb * gb * b_bytes);
+                            if (leader) mbar_expect_tx(fb, (PAIR ? 2u : 1u) * (uint32_t)(ng * b_bytes));
+                            for (int j = 0; j < ng; ++j) {
+                                const int wi = p.taps[t.phase][t0 + j].wi;
+                                if (PAIR) tma_load_4d_pair(db + j * b_bytes, &mapB, fb, (second ? c0s : 0) + cc, ncol, wi, 0);
+                                else tma_load_4d(db + j * b_bytes, &mapB, fb, (second ? c0s : 0) + cc, ncol, wi, 0);
+                            }
+                            if (++sb == nb_stages) { sb = 0; pb ^= 1; }
+                        }
+                    }
+                }
+            } else {
+            int stage = 0; uint32_t phase = 0;
             for (int tile = item0; tile < total; tile += item_step) {
                 const TileCoord t = decode_tile(p, tile, m_units, per_unit, rank);
                 const int ntap = p.ntaps[t.phase];
-                const int n_outer = p.halo ? n_chunks : ntap * n_chunks;
-                const int n_inner = p.halo ? ntap : 1;
-                for (int o = 0; o < n_outer; ++o) {
-                    const int cb = p.halo ? o : o % n_chunks;
-                    const bool second = cb >= nch0;
-                    const int cc = (second ? cb - nch0 : cb) * 64;
-                    const CUtensorMap* mapA = second ? &mapA1 : &mapA0;
-                    // ---- activations
-                    mbar_wait(emptyA0 + 8 * sa, pa ^ 1);
-                    const uint32_t fa = fullA0 + 8 * sa;
-                    const uint32_t da = smem_u32(smem + (size_t)sa * a_bytes);
-                    if (leader) mbar_expect_tx(fa, txmul * (uint32_t)(p.planes * a_box_bytes));
-                    if (p.halo) {
-                        for (int pl = 0; pl < p.planes; ++pl) {
-                            if (PAIR) tma_load_5d_pair(da + pl * a_plane_bytes, mapA, fa, cc, t.x0 - p.hx0, t.y0 - p.hy0, t.n0, pl);
-                            else tma_load_5d(da + pl * a_plane_bytes, mapA, fa, cc, t.x0 - p.hx0, t.y0 - p.hy0, t.n0, pl);
+                for (int tp = 0; tp < ntap; ++tp) {
+                    const TcTap tap = p.taps[t.phase][tp];
+                    for (int cb = 0; cb < nch0 + nch1; ++cb) {
+                        const bool second = cb >= nch0;
+                        const int cc = (second ? cb - nch0 : cb) * 64;
+                        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                        const uint32_t fb = full0 + 8 * stage;
+                        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                        const bool doA = !(p.exp_flags & 1), doB = !(p.exp_flags & 2);
+                        const uint32_t tx = (doA ? a_bytes : 0) + (doB ? b_bytes : 0);
+                        if (PAIR) {
+                            // the leader's barrier collects the bytes of both CTAs
+                            if (leader) mbar_expect_tx(fb, 2u * tx);
+                            if (doA) tma_load_5d_pair(sa, second ? &mapA1 : &mapA0, fb, cc, t.x0 + tap.dx, t.y0 + tap.dy, t.n0, 0);
+                            if (doB) tma_load_4d_pair(sa + a_bytes, &mapB, fb, (second ? p.c0 : 0) + cc,
+                                                      t.n_idx * p.n_t + rank * (p.n_t / 2), tap.wi, 0);
+                        } else {
+                            mbar_expect_tx(fb, tx);
+                            if (doA) tma_load_5d(sa, second ? &mapA1 : &mapA0, fb, cc, t.x0 + tap.dx, t.y0 + tap.dy, t.n0, 0);
+                            if (doB) tma_load_4d(sa + a_bytes, &mapB, fb, (second ? p.c0 : 0) + cc, t.n_idx * p.n_t, tap.wi, 0);
                         }
-                    } else {
-                        const TcTap tap = p.taps[t.phase][o / n_chunks];
-                        if (PAIR) tma_load_5d_pair(da, mapA, fa, cc, t.x0 + tap.dx, t.y0 + tap.dy, t.n0, 0);
-                        else tma_load_5d(da, mapA, fa, cc, t.x0 + tap.dx, t.y0 + tap.dy, t.n0, 0);
-                    }
-                    if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
-                    // ---- weights
-                    for (int i = 0; i < n_inner; ++i) {
-                        const TcTap tap = p.taps[t.phase][p.halo ? i : o / n_chunks];
-                        mbar_wait(emptyB0 + 8 * sb, pb ^ 1);
-                        const uint32_t fb = fullB0 + 8 * sb;
-                        const uint32_t db = smem_u32(smem_b + (size_t)sb * b_bytes);
-                        if (leader) mbar_expect_tx(fb, txmul * (uint32_t)b_bytes);
-                        if (PAIR) tma_load_4d_pair(db, &mapB, fb, (second ? p.c0 : 0) + cc, t.n_idx * p.n_t + rank * (p.n_t / 2), tap.wi, 0);
-                        else tma_load_4d(db, &mapB, fb, (second ? p.c0 : 0) + cc, t.n_idx * p.n_t, tap.wi, 0);
-                        if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                 }
+            }
             }
         }
     } else if (warp == 1) {
         if (lane == 0 && leader) {
             // ================= MMA issuer (leader CTA only in pair mode) =================
             const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_t >> 3) << 17) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
-            const uint32_t a_sbo = p.halo ? (uint32_t)p.pw * 128u : 1024u;     // halo: consecutive 8-pixel rows are one patch row apart
-            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
             int acc = 0; uint32_t acc_phase = 0;
+            if constexpr (HALO) {
+                const int pw = p.pw, hx0 = p.hx0, hy0 = p.hy0, n_chunks = nch0 + nch1, c0s = p.c0, c1s = p.c1;
+                const uint32_t a_sbo = (uint32_t)pw * 128u;         // consecutive 8-pixel rows are one patch row apart
+                int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+                for (int tile = item0; tile < total; tile += item_step) {
+                    const TileCoord t = decode_tile(p, tile, m_units, per_unit, rank);
+                    const int ntap = p.ntaps[t.phase];
+                    mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccStride);
+                    uint32_t accumulate = 0;
+                    for (int cb = 0; cb < n_chunks; ++cb) {
+                        const bool second = cb >= nch0;
+                        const int kvalid = min(64, (second ? c1s : c0s) - (second ? cb - nch0 : cb) * 64);
+                        const int nk = (kvalid + 15) >> 4;
+                        mbar_wait(full0 + 8 * sa, pa);
+                        tc_fence_after();
+                        const uint32_t abase = smem_u32(smem + (size_t)sa * stage_bytes);
+                        for (int t0 = 0; t0 < ntap; t0 += gb) {
+                            const int ng = min(gb, ntap - t0);
+                            mbar_wait(fullB0 + 8 * sb, pb);
+                            tc_fence_after();
+                            const uint32_t bbase = smem_u32(smem_b + (size_t)sb * gb * b_bytes);
+                            for (int j = 0; j < ng; ++j) {
+                                const TcTap tap = p.taps[t.phase][t0 + j];
+                                const uint32_t sa_t = abase + (uint32_t)((tap.dy + hy0) * pw + tap.dx + hx0) * 128u;
+                                const uint32_t sb_t = bbase + j * b_bytes;
+                                for (int k = 0; k < nk; ++k) {
+                                    const uint64_t ah = umma_desc_sbo(sa_t + k * 32, a_sbo), bh = umma_desc(sb_t + k * 32);
+                                    if (PAIR) umma_f16_pair(tmem_d, ah, bh, idesc, accumulate); else umma_f16(tmem_d, ah, bh, idesc, accumulate);
+                                    accumulate = 1;
+                                    if (planes == 2) {
+                                        const uint64_t al = umma_desc_sbo(sa_t + a_plane_bytes + k * 32, a_sbo);
+                                        const uint64_t bl = umma_desc(sb_t + b_plane_bytes + k * 32);
+                                        if (PAIR) { umma_f16_pair(tmem_d, ah, bl, idesc, 1); umma_f16_pair(tmem_d, al, bh, idesc, 1); }
+                                        else { umma_f16(tmem_d, ah, bl, idesc, 1); umma_f16(tmem_d, al, bh, idesc, 1); }
+                                    }
+                                }
+                            }
+                            if (PAIR) umma_commit_pair(emptyB0 + 8 * sb); else umma_commit(emptyB0 + 8 * sb);
+                            if (++sb == nb_stages) { sb = 0; pb ^= 1; }
+                        }
+                        if (PAIR) umma_commit_pair(empty0 + 8 * sa); else umma_commit(empty0 + 8 * sa);
+                        if (++sa == n_stages) { sa = 0; pa ^= 1; }
+                    }
+                    if (PAIR) umma_commit_pair(tfull0 + 8 * acc); else umma_commit(tfull0 + 8 * acc);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            } else {
+            int stage = 0; uint32_t phase = 0;
             for (int tile = item0; tile < total; tile += item_step) {
                 const TileCoord t = decode_tile(p, tile, m_units, per_unit, rank);
                 const int ntap = p.ntaps[t.phase];
-                const int n_outer = p.halo ? n_chunks : ntap * n_chunks;
-                const int n_inner = p.halo ? ntap : 1;
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccStride);
                 uint32_t accumulate = 0;
-                for (int o = 0; o < n_outer; ++o) {
-                    const int cb = p.halo ? o : o % n_chunks;
-                    const bool second = cb >= nch0;
-                    const int cc = (second ? cb - nch0 : cb) * 64;
-                    const int kvalid = min(64, (second ? p.c1 : p.c0) - cc);
-                    const int nk = (p.exp_flags & 4) ? 1 : (kvalid + 15) >> 4;
-                    mbar_wait(fullA0 + 8 * sa, pa);
-                    tc_fence_after();
-                    const uint32_t abase = smem_u32(smem + (size_t)sa * a_bytes);
-                    for (int i = 0; i < n_inner; ++i) {
-                        uint32_t aoff = 0;
-                        if (p.halo) {
-                            const TcTap tap = p.taps[t.phase][i];
-                            aoff = (uint32_t)((tap.dy + p.hy0) * p.pw + tap.dx + p.hx0) * 128u;
-                        }
-                        mbar_wait(fullB0 + 8 * sb, pb);
+                for (int tp = 0; tp < ntap; ++tp) {
+                    for (int cb = 0; cb < nch0 + nch1; ++cb) {
+                        const bool second = cb >= nch0;
+                        const int cc = (second ? cb - nch0 : cb) * 64;
+                        const int kvalid = min(64, (second ? p.c1 : p.c0) - cc);
+                        const int nk = (p.exp_flags & 4) ? 1 : (kvalid + 15) >> 4;
+                        mbar_wait(full0 + 8 * stage, phase);
                         tc_fence_after();
-                        const uint32_t bbase = smem_u32(smem_b + (size_t)sb * b_bytes);
+                        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                        const uint32_t sb = sa + a_bytes;
                         for (int k = 0; k < nk; ++k) {
-                            const uint64_t ah = umma_desc_a(abase + aoff + k * 32, a_sbo, p.desc_mode), bh = umma_desc(bbase + k * 32);
+                            const uint64_t ah = umma_desc(sa + k * 32), bh = umma_desc(sb + k * 32);
                             if (PAIR) umma_f16_pair(tmem_d, ah, bh, idesc, accumulate); else umma_f16(tmem_d, ah, bh, idesc, accumulate);
                             accumulate = 1;
                             if (p.planes == 2) {
-                                const uint64_t al = umma_desc_a(abase + a_plane_bytes + aoff + k * 32, a_sbo, p.desc_mode);
-                                const uint64_t bl = umma_desc(bbase + b_plane_bytes + k * 32);
+                                const uint64_t al = umma_desc(sa + kAPlaneBytes + k * 32);
+                                const uint64_t bl = umma_desc(sb + b_plane_bytes + k * 32);
                                 if (PAIR) { umma_f16_pair(tmem_d, ah, bl, idesc, 1); umma_f16_pair(tmem_d, al, bh, idesc, 1); }
                                 else { umma_f16(tmem_d, ah, bl, idesc, 1); umma_f16(tmem_d, al, bh, idesc, 1); }
                             }
                         }
-                        // frees the weight slot (in both CTAs) when these MMAs retire
-                        if (PAIR) umma_commit_pair(emptyB0 + 8 * sb); else umma_commit(emptyB0 + 8 * sb);
-                        if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+                        // frees the smem slot (in both CTAs) when these MMAs retire
+                        if (PAIR) umma_commit_pair(empty0 + 8 * stage); else umma_commit(empty0 + 8 * stage);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
-                    if (PAIR) umma_commit_pair(emptyA0 + 8 * sa); else umma_commit(emptyA0 + 8 * sa);
-                    if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
                 }
                 // accumulator ready for the epilogue (of both CTAs)
                 if (PAIR) umma_commit_pair(tfull0 + 8 * acc); else umma_commit(tfull0 + 8 * acc);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
             }
         }
     } else {
@@ -496,38 +561,43 @@ EncodeTiledFn encode_fn() {
 
 }  // namespace
 
-size_t tc_conv_a_stage_bytes(const TcConvParams& p) {
-    const size_t box = p.halo ? (size_t)p.ph * p.pw * 128 : (size_t)kAPlaneBytes;
-    return (size_t)p.planes * ((box + 1023) & ~(size_t)1023);
-}
-size_t tc_conv_b_stage_bytes(const TcConvParams& p) {
-    return (size_t)p.planes * (size_t)(p.pair ? p.n_t / 2 : p.n_t) * 128;
-}
 size_t tc_conv_fixed_bytes(const TcConvParams& p) {
     const size_t cpad = (size_t)p.n_ntiles * p.n_t;
     const size_t tables = ((size_t)9 * p.skip_c * cpad + (p.top_w ? cpad * p.top_k + 4 : 0)) * sizeof(float);
-    return (2 * (size_t)(p.a_stages + p.b_stages) + 4) * 8 + 16 + tables + 1024;
+    return (2 * (size_t)(p.stages + (p.halo ? p.b_stages : 0)) + 4) * 8 + 16 + tables + 1024;
 }
+size_t tc_conv_a_bytes(const TcConvParams& p) {
+    const size_t box = p.halo ? (((size_t)p.ph * p.pw * 128 + 1023) & ~(size_t)1023) : (size_t)kAPlaneBytes;
+    return (size_t)p.planes * box;
+}
+size_t tc_conv_b_bytes(const TcConvParams& p) { return (size_t)p.planes * (size_t)(p.pair ? p.n_t / 2 : p.n_t) * 128; }
 size_t tc_conv_smem_bytes(const TcConvParams& p) {
-    return p.a_stages * tc_conv_a_stage_bytes(p) + p.b_stages * tc_conv_b_stage_bytes(p) + tc_conv_fixed_bytes(p);
+    if (p.halo) return p.stages * tc_conv_a_bytes(p) + (size_t)p.b_stages * p.gb * tc_conv_b_bytes(p) + tc_conv_fixed_bytes(p);
+    return p.stages * (tc_conv_a_bytes(p) + tc_conv_b_bytes(p)) + tc_conv_fixed_bytes(p);
 }
 
-template <int SKIPC, bool PAIR>
+template <int SKIPC, bool PAIR, bool HALO>
 static cudaError_t configure_one() {
-    return cudaFuncSetAttribute(tc_conv_kernel<SKIPC, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return cudaFuncSetAttribute(tc_conv_kernel<SKIPC, PAIR, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
-cudaError_t tc_conv_configure() {
-    cudaError_t e = configure_one<0, false>();
-    if (e == cudaSuccess) e = configure_one<1, false>();
-    if (e == cudaSuccess) e = configure_one<2, false>();
-    if (e == cudaSuccess) e = configure_one<0, true>();
-    if (e == cudaSuccess) e = configure_one<1, true>();
-    if (e == cudaSuccess) e = configure_one<2, true>();
+template <int SKIPC>
+static cudaError_t configure_skipc() {
+    cudaError_t e = configure_one<SKIPC, false, false>();
+    if (e == cudaSuccess) e = configure_one<SKIPC, true, false>();
+    if (e == cudaSuccess) e = configure_one<SKIPC, false, true>();
+    if (e == cudaSuccess) e = configure_one<SKIPC, true, true>();
     return e;
 }
 
-template <int SKIPC, bool PAIR>
+cudaError_t tc_conv_configure() {
+    cudaError_t e = configure_skipc<0>();
+    if (e == cudaSuccess) e = configure_skipc<1>();
+    if (e == cudaSuccess) e = configure_skipc<2>();
+    return e;
+}
+
+template <int SKIPC, bool PAIR, bool HALO>
 static cudaError_t launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcConvParams& p,
                               int grid, size_t smem, cudaStream_t s) {
     cudaLaunchConfig_t cfg = {};
@@ -536,7 +606,14 @@ static cudaError_t launch_one(const CUtensorMap& a0, const CUtensorMap& a1, cons
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, tc_conv_kernel<SKIPC, PAIR>, a0, a1, b, p);
+    return cudaLaunchKernelEx(&cfg, tc_conv_kernel<SKIPC, PAIR, HALO>, a0, a1, b, p);
+}
+
+template <int SKIPC>
+static cudaError_t launch_skipc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcConvParams& p,
+                                int grid, size_t smem, cudaStream_t s) {
+    if (p.pair) return p.halo ? launch_one<SKIPC, true, true>(a0, a1, b, p, grid, smem, s) : launch_one<SKIPC, true, false>(a0, a1, b, p, grid, smem, s);
+    return p.halo ? launch_one<SKIPC, false, true>(a0, a1, b, p, grid, smem, s) : launch_one<SKIPC, false, false>(a0, a1, b, p, grid, smem, s);
 }
 
 cudaError_t launch_tc_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcConvParams& p,
@@ -552,15 +629,9 @@ cudaError_t launch_tc_conv(const CUtensorMap& a0, const CUtensorMap& a1, const C
     if (smem < 120 * 1024) smem = 120 * 1024;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     const int skipc = p.skip_src ? p.skip_c : 0;
-    if (p.pair) {
-        if (skipc == 0) return launch_one<0, true>(a0, a1, b, p, grid, smem, s);
-        if (skipc == 1) return launch_one<1, true>(a0, a1, b, p, grid, smem, s);
-        if (skipc == 2) return launch_one<2, true>(a0, a1, b, p, grid, smem, s);
-    } else {
-        if (skipc == 0) return launch_one<0, false>(a0, a1, b, p, grid, smem, s);
-        if (skipc == 1) return launch_one<1, false>(a0, a1, b, p, grid, smem, s);
-        if (skipc == 2) return launch_one<2, false>(a0, a1, b, p, grid, smem, s);
-    }
+    if (skipc == 0) return launch_skipc<0>(a0, a1, b, p, grid, smem, s);
+    if (skipc == 1) return launch_skipc<1>(a0, a1, b, p, grid, smem, s);
+    if (skipc == 2) return launch_skipc<2>(a0, a1, b, p, grid, smem, s);
     return cudaErrorInvalidValue;
 }
 

@@ -435,40 +435,39 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     tp.planes = planes;
     {
         const char* e = getenv("UMX_TC_PAIR");
-        tp.pair = (e ? atoi(e) : 1) && ((tp.n_t / 2) % 8 == 0) ? 1 : 0;
+        tp.pair = (e ? atoi(e) : 1) && (tp.n_t % 32 == 0 || tp.n_t % 16 == 0) && ((tp.n_t / 2) % 8 == 0) ? 1 : 0;
     }
     // halo mode for the high-resolution layers: A is fetched once per 64-channel slab as a pixel patch
     // (instead of once per tap), cutting the L2->SM traffic of A by ~6x
     {
         const char* e = getenv("UMX_TC_HALO");
-        const int want = e ? atoi(e) : 0;
-        if (want && a0.w >= 16 && a0.h >= 16) {
+        if ((e ? atoi(e) : 1) && a0.w >= 16 && a0.h >= 16) {
             tp.halo = 1; tp.bw = 8; tp.bh = 16; tp.bn = 1;
             tp.hx0 = tt.hx0; tp.hy0 = tt.hy0;
             tp.pw = tp.bw + tt.hx0 + tt.hx1; tp.ph = tp.bh + tt.hy0 + tt.hy1;
-            tp.desc_mode = want == 2 ? 1 : 0;
         }
     }
     {
-        TcConvParams probe = tp; probe.a_stages = probe.b_stages = 0;
         const size_t cpad = (size_t)tp.n_ntiles * tp.n_t;
         const size_t tables = (op.skip_mode ? (size_t)9 * h->bufs[T.src0].c * cpad * 4 : 0) + (op.fuse_top >= 0 ? (cpad * h->K + 8) * 4 : 0);
-        const size_t budget = 227 * 1024 - 1024 - tc_conv_fixed_bytes(probe) - 512 - tables;
-        const size_t ab = tc_conv_a_stage_bytes(tp), bb = tc_conv_b_stage_bytes(tp);
+        const size_t budget = 227 * 1024 - 2048 - 512 - tables;
+        const size_t ab = tc_conv_a_bytes(tp), bb = tc_conv_b_bytes(tp);
         if (tp.halo) {
-            tp.a_stages = 2;
-            tp.b_stages = (int)std::min<size_t>(8, (budget - 2 * ab) / bb);
-        } else {
-            tp.a_stages = tp.b_stages = (int)std::min<size_t>(6, budget / (ab + bb));
+            tp.stages = 2;
+            tp.gb = 3;
+            if (const char* e = getenv("UMX_TC_GB")) tp.gb = std::max(1, std::min(9, atoi(e)));
+            while (tp.gb > 1 && budget < 2 * ab + 2 * (size_t)tp.gb * bb) tp.gb--;
+            tp.b_stages = (int)std::min<size_t>(6, (budget - 2 * ab) / ((size_t)tp.gb * bb));
+            if (tp.b_stages < 2) { tp.halo = 0; tp.bw = std::min(a0.w, 16); tp.bh = std::min(a0.h, 128 / tp.bw); tp.bn = 128 / (tp.bw * tp.bh); }
         }
-        if (const char* e = getenv("UMX_TC_STAGES")) {
-            const int cap = std::max(2, atoi(e));
-            tp.b_stages = std::min(tp.b_stages, cap);
-            if (!tp.halo) tp.a_stages = tp.b_stages;
-        }
-        if (const char* e = getenv("UMX_TC_EXP")) tp.exp_flags = atoi(e);
-        if (tp.a_stages < 2 || tp.b_stages < 2) { set_error("%s: pipeline does not fit shared memory", op.name.c_str()); return UMX_EINVAL; }
+        if (!tp.halo) tp.stages = (int)std::min<size_t>(6, budget / (tc_conv_a_bytes(tp) + bb));
     }
+    if (const char* e = getenv("UMX_TC_EXP")) tp.exp_flags = atoi(e);
+    if (const char* e = getenv("UMX_TC_STAGES")) {
+        const int cap = std::max(2, atoi(e));
+        if (tp.halo) tp.b_stages = std::min(tp.b_stages, cap); else tp.stages = std::min(tp.stages, cap);
+    }
+    if (tp.stages < 2) { set_error("%s: pipeline does not fit shared memory", op.name.c_str()); return UMX_EINVAL; }
     tp.act = sp.act; tp.leaky = kLeaky; tp.pool = sp.pool ? 1 : 0;
     float* d = nullptr;
     if (sp.has_bias) { UMX_TRY(upload(h, sp.bias, &d)); tp.bias = d; }

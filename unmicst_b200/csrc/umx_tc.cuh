@@ -21,10 +21,10 @@ struct TcConvParams {
     int32_t ntaps[4];
     TcTap   taps[4][9];
     int32_t planes;              // 1: fp16 operands, 1 MMA/product; 2: hi/lo split, 3 MMAs/product
-    int32_t a_stages, b_stages;  // smem ring depths (activations / weights)
+    int32_t stages;              // smem pipeline depth (halo mode: patch slots)
     int32_t halo;                // 1: one (bh+halo) x (bw+halo) pixel patch per 64-channel slab serves every tap
     int32_t pw, ph, hx0, hy0;    // patch size and left/top halo (halo mode)
-    int32_t desc_mode;           // 1: put (addr>>7)&7 into the A descriptor's base-offset field
+    int32_t b_stages, gb;        // halo mode: weight ring depth, taps per weight slot
     int32_t exp_flags;           // timing experiments only (results invalid): 1 no A loads, 2 no B loads, 4 one MMA per stage, 8 no epilogue math
     int32_t pair;                // 1: CTA pairs, tcgen05.mma.cta_group::2 (M = 256 across two SMs)
     int32_t act;                 // umx::Act
@@ -48,8 +48,8 @@ struct TcConvParams {
 };
 
 size_t tc_conv_smem_bytes(const TcConvParams& p);
-size_t tc_conv_a_stage_bytes(const TcConvParams& p);
-size_t tc_conv_b_stage_bytes(const TcConvParams& p);
+size_t tc_conv_a_bytes(const TcConvParams& p);
+size_t tc_conv_b_bytes(const TcConvParams& p);
 size_t tc_conv_fixed_bytes(const TcConvParams& p);
 cudaError_t tc_conv_configure();
 cudaError_t launch_tc_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
