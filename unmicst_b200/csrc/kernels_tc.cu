@@ -55,6 +55,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (++spins > kSpinLimit) { printf("umx tc_conv: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
     }
 }
+// Polite wait for threads that are not on the critical path (epilogue, producer): back off between polls so the
+// MMA-issuing thread's barrier traffic is not contended.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(32);
+        if (++spins > (kSpinLimit >> 4)) { printf("umx tc_conv: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -177,7 +186,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int a_bytes = planes * a_plane_bytes;
     const int b_plane_bytes = (PAIR ? p.n_t / 2 : p.n_t) * 128;     // pair mode: each CTA stages half of the N rows
     const int b_bytes = planes * b_plane_bytes;
-    const int stage_bytes = HALO ? a_bytes : a_bytes + b_bytes;
+    const int ks = HALO ? 1 : p.kslab;                               // plain mode: 64-channel slabs per ring slot
+    const int slab_bytes = a_bytes + b_bytes;
+    const int stage_bytes = HALO ? a_bytes : ks * slab_bytes;
     const int n_stages = p.stages;                                   // plain: ring slots; halo: patch slots
     const int nb_stages = HALO ? p.b_stages : 0;
     const int gb = HALO ? p.gb : 1;
@@ -290,24 +301,25 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const int ntap = p.ntaps[t.phase];
                 for (int tp = 0; tp < ntap; ++tp) {
                     const TcTap tap = p.taps[t.phase][tp];
-                    for (int cb = 0; cb < nch0 + nch1; ++cb) {
-                        const bool second = cb >= nch0;
-                        const int cc = (second ? cb - nch0 : cb) * 64;
+                    for (int c0 = 0; c0 < nch0 + nch1; c0 += ks) {
+                        const int ns = min(ks, nch0 + nch1 - c0);
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
                         const uint32_t fb = full0 + 8 * stage;
-                        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                        const bool doA = !(p.exp_flags & 1), doB = !(p.exp_flags & 2);
-                        const uint32_t tx = (doA ? a_bytes : 0) + (doB ? b_bytes : 0);
-                        if (PAIR) {
-                            // the leader's barrier collects the bytes of both CTAs
-                            if (leader) mbar_expect_tx(fb, 2u * tx);
-                            if (doA) tma_load_5d_pair(sa, second ? &mapA1 : &mapA0, fb, cc, t.x0 + tap.dx, t.y0 + tap.dy, t.n0, 0);
-                            if (doB) tma_load_4d_pair(sa + a_bytes, &mapB, fb, (second ? p.c0 : 0) + cc,
-                                                      t.n_idx * p.n_t + rank * (p.n_t / 2), tap.wi, 0);
-                        } else {
-                            mbar_expect_tx(fb, tx);
-                            if (doA) tma_load_5d(sa, second ? &mapA1 : &mapA0, fb, cc, t.x0 + tap.dx, t.y0 + tap.dy, t.n0, 0);
-                            if (doB) tma_load_4d(sa + a_bytes, &mapB, fb, (second ? p.c0 : 0) + cc, t.n_idx * p.n_t, tap.wi, 0);
+                        const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
+                        if (leader) mbar_expect_tx(fb, (PAIR ? 2u : 1u) * (uint32_t)(ns * slab_bytes));
+                        for (int j = 0; j < ns; ++j) {
+                            const int cb = c0 + j;
+                            const bool second = cb >= nch0;
+                            const int cc = (second ? cb - nch0 : cb) * 64;
+                            const uint32_t sa = sbase + j * slab_bytes;
+                            if (PAIR) {
+                                tma_load_5d_pair(sa, second ? &mapA1 : &mapA0, fb, cc, t.x0 + tap.dx, t.y0 + tap.dy, t.n0, 0);
+                                tma_load_4d_pair(sa + a_bytes, &mapB, fb, (second ? p.c0 : 0) + cc,
+                                                 t.n_idx * p.n_t + rank * (p.n_t / 2), tap.wi, 0);
+                            } else {
+                                tma_load_5d(sa, second ? &mapA1 : &mapA0, fb, cc, t.x0 + tap.dx, t.y0 + tap.dy, t.n0, 0);
+                                tma_load_4d(sa + a_bytes, &mapB, fb, (second ? p.c0 : 0) + cc, t.n_idx * p.n_t, tap.wi, 0);
+                            }
                         }
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
@@ -378,14 +390,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccStride);
                 uint32_t accumulate = 0;
                 for (int tp = 0; tp < ntap; ++tp) {
-                    for (int cb = 0; cb < nch0 + nch1; ++cb) {
+                    for (int c0 = 0; c0 < nch0 + nch1; c0 += ks) {
+                        const int ns = min(ks, nch0 + nch1 - c0);
+                        mbar_wait(full0 + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
+                        for (int j = 0; j < ns; ++j) {
+                        const int cb = c0 + j;
                         const bool second = cb >= nch0;
                         const int cc = (second ? cb - nch0 : cb) * 64;
                         const int kvalid = min(64, (second ? p.c1 : p.c0) - cc);
                         const int nk = (p.exp_flags & 4) ? 1 : (kvalid + 15) >> 4;
-                        mbar_wait(full0 + 8 * stage, phase);
-                        tc_fence_after();
-                        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                        const uint32_t sa = sbase + j * slab_bytes;
                         const uint32_t sb = sa + a_bytes;
                         for (int k = 0; k < nk; ++k) {
                             const uint64_t ah = umma_desc(sa + k * 32), bh = umma_desc(sb + k * 32);
@@ -397,6 +413,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                                 if (PAIR) { umma_f16_pair(tmem_d, ah, bl, idesc, 1); umma_f16_pair(tmem_d, al, bh, idesc, 1); }
                                 else { umma_f16(tmem_d, ah, bl, idesc, 1); umma_f16(tmem_d, al, bh, idesc, 1); }
                             }
+                        }
                         }
                         // frees the smem slot (in both CTAs) when these MMAs retire
                         if (PAIR) umma_commit_pair(empty0 + 8 * stage); else umma_commit(empty0 + 8 * stage);
@@ -573,7 +590,7 @@ size_t tc_conv_a_bytes(const TcConvParams& p) {
 size_t tc_conv_b_bytes(const TcConvParams& p) { return (size_t)p.planes * (size_t)(p.pair ? p.n_t / 2 : p.n_t) * 128; }
 size_t tc_conv_smem_bytes(const TcConvParams& p) {
     if (p.halo) return p.stages * tc_conv_a_bytes(p) + (size_t)p.b_stages * p.gb * tc_conv_b_bytes(p) + tc_conv_fixed_bytes(p);
-    return p.stages * (tc_conv_a_bytes(p) + tc_conv_b_bytes(p)) + tc_conv_fixed_bytes(p);
+    return p.stages * (size_t)(p.kslab > 0 ? p.kslab : 1) * (tc_conv_a_bytes(p) + tc_conv_b_bytes(p)) + tc_conv_fixed_bytes(p);
 }
 
 template <int SKIPC, bool PAIR, bool HALO>

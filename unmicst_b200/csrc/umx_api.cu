@@ -460,7 +460,15 @@ int lower_conv_tc(umx_handle* h, Op& op) {
             tp.b_stages = (int)std::min<size_t>(6, (budget - 2 * ab) / ((size_t)tp.gb * bb));
             if (tp.b_stages < 2) { tp.halo = 0; tp.bw = std::min(a0.w, 16); tp.bh = std::min(a0.h, 128 / tp.bw); tp.bn = 128 / (tp.bw * tp.bh); }
         }
-        if (!tp.halo) tp.stages = (int)std::min<size_t>(6, budget / (tc_conv_a_bytes(tp) + bb));
+        tp.kslab = 1;
+        if (!tp.halo) {
+            // single precision issues one MMA per K step: put two slabs behind each barrier round trip
+            const int n_chunks = (tp.c0 + 63) / 64 + (tp.c1 + 63) / 64;
+            tp.kslab = std::min(planes == 1 ? 2 : 1, n_chunks);
+            if (const char* e = getenv("UMX_TC_KSLAB")) tp.kslab = std::max(1, std::min(std::min(4, n_chunks), atoi(e)));
+            while (tp.kslab > 1 && budget / (tp.kslab * (tc_conv_a_bytes(tp) + bb)) < 3) tp.kslab--;
+            tp.stages = (int)std::min<size_t>(6, budget / (tp.kslab * (tc_conv_a_bytes(tp) + bb)));
+        }
     }
     if (const char* e = getenv("UMX_TC_EXP")) tp.exp_flags = atoi(e);
     if (const char* e = getenv("UMX_TC_STAGES")) {

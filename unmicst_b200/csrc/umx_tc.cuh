@@ -25,6 +25,7 @@ struct TcConvParams {
     int32_t halo;                // 1: one (bh+halo) x (bw+halo) pixel patch per 64-channel slab serves every tap
     int32_t pw, ph, hx0, hy0;    // patch size and left/top halo (halo mode)
     int32_t b_stages, gb;        // halo mode: weight ring depth, taps per weight slot
+    int32_t kslab;               // plain mode: 64-channel slabs per ring slot (more MMAs per barrier round trip)
     int32_t exp_flags;           // timing experiments only (results invalid): 1 no A loads, 2 no B loads, 4 one MMA per stage, 8 no epilogue math
     int32_t pair;                // 1: CTA pairs, tcgen05.mma.cta_group::2 (M = 256 across two SMs)
     int32_t act;                 // umx::Act
