@@ -170,8 +170,8 @@ __device__ __forceinline__ float act_fn(float v, int act, float leaky) {
     return v;
 }
 
-// SKIPC = channels of the narrow fp32 skip source folded into the epilogue (0 = none).
-template <int SKIPC, bool PAIR, bool HALO>
+// SKIPC = channels of the narrow fp32 source folded into the epilogue (0 = none), SKT = its tap count.
+template <int SKIPC, int SKT, bool PAIR, bool HALO>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ TcConvParams p) {
@@ -205,10 +205,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     // (rows padded with zeros to cpad = n_ntiles * n_t columns so the epilogue needs no channel guards)
     const int cpad = p.n_ntiles * p.n_t;
     float* s_skipw = reinterpret_cast<float*>(tmem_slot + 4);
-    float* s_topw = s_skipw + 9 * SKIPC * cpad;
+    float* s_topw = s_skipw + SKT * SKIPC * cpad;
     float* s_topb = s_topw + (p.top_w ? cpad * p.top_k : 0);
     if (SKIPC > 0)
-        for (int i = threadIdx.x; i < 9 * SKIPC * cpad; i += kThreads) {
+        for (int i = threadIdx.x; i < SKT * SKIPC * cpad; i += kThreads) {
             const int c = i % cpad;
             s_skipw[i] = c < p.cout ? p.skip_w[(i / cpad) * p.cout + c] : 0.f;
         }
@@ -260,6 +260,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             // ================= TMA producer =================
             if constexpr (HALO) {
                 const int hx0 = p.hx0, hy0 = p.hy0, n_chunks = nch0 + nch1, c0s = p.c0, n_t = p.n_t;
+                const bool a1c = p.a1_center != 0; const int ctap = p.center_tap;
                 const uint32_t txA = (PAIR ? 2u : 1u) * (uint32_t)(planes * a_box_bytes);
                 int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
                 for (int tile = item0; tile < total; tile += item_step) {
@@ -279,8 +280,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             else tma_load_5d(da + pl * a_plane_bytes, mapA, fa, cc, t.x0 - hx0, t.y0 - hy0, t.n0, pl);
                         }
                         if (++sa == n_stages) { sa = 0; pa ^= 1; }
-                        for (int t0 = 0; t0 < ntap; t0 += gb) {
-                            const int ng = min(gb, ntap - t0);
+                        const int tb = (second && a1c) ? ctap : 0, te = (second && a1c) ? ctap + 1 : ntap;
+                        for (int t0 = tb; t0 < te; t0 += gb) {
+                            const int ng = min(gb, te - t0);
                             mbar_wait(emptyB0 + 8 * sb, pb ^ 1);
                             const uint32_t fb = fullB0 + 8 * sb;
                             const uint32_t db = smem_u32(smem_b + (size_t)sb * gb * b_bytes);
@@ -301,8 +303,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const int ntap = p.ntaps[t.phase];
                 for (int tp = 0; tp < ntap; ++tp) {
                     const TcTap tap = p.taps[t.phase][tp];
-                    for (int c0 = 0; c0 < nch0 + nch1; c0 += ks) {
-                        const int ns = min(ks, nch0 + nch1 - c0);
+                    const int nchunks_tp = nch0 + ((p.a1_center && tp != p.center_tap) ? 0 : nch1);
+                    for (int c0 = 0; c0 < nchunks_tp; c0 += ks) {
+                        const int ns = min(ks, nchunks_tp - c0);
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
                         const uint32_t fb = full0 + 8 * stage;
                         const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
@@ -334,6 +337,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             int acc = 0; uint32_t acc_phase = 0;
             if constexpr (HALO) {
                 const int pw = p.pw, hx0 = p.hx0, hy0 = p.hy0, n_chunks = nch0 + nch1, c0s = p.c0, c1s = p.c1;
+                const bool a1c = p.a1_center != 0; const int ctap = p.center_tap;
                 const uint32_t a_sbo = (uint32_t)pw * 128u;         // consecutive 8-pixel rows are one patch row apart
                 int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
                 for (int tile = item0; tile < total; tile += item_step) {
@@ -350,8 +354,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         mbar_wait(full0 + 8 * sa, pa);
                         tc_fence_after();
                         const uint32_t abase = smem_u32(smem + (size_t)sa * stage_bytes);
-                        for (int t0 = 0; t0 < ntap; t0 += gb) {
-                            const int ng = min(gb, ntap - t0);
+                        const int tb = (second && a1c) ? ctap : 0, te = (second && a1c) ? ctap + 1 : ntap;
+                        for (int t0 = tb; t0 < te; t0 += gb) {
+                            const int ng = min(gb, te - t0);
                             mbar_wait(fullB0 + 8 * sb, pb);
                             tc_fence_after();
                             const uint32_t bbase = smem_u32(smem_b + (size_t)sb * gb * b_bytes);
@@ -390,8 +395,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccStride);
                 uint32_t accumulate = 0;
                 for (int tp = 0; tp < ntap; ++tp) {
-                    for (int c0 = 0; c0 < nch0 + nch1; c0 += ks) {
-                        const int ns = min(ks, nch0 + nch1 - c0);
+                    const int nchunks_tp = nch0 + ((p.a1_center && tp != p.center_tap) ? 0 : nch1);
+                    for (int c0 = 0; c0 < nchunks_tp; c0 += ks) {
+                        const int ns = min(ks, nchunks_tp - c0);
                         mbar_wait(full0 + 8 * stage, phase);
                         tc_fence_after();
                         const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
@@ -441,12 +447,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             else if (p.os == 2) { oh = p.in_h * 2; ow = p.in_w * 2; oy = 2 * y + (t.phase >> 1); ox = 2 * x + (t.phase & 1); }
             else { oh = p.in_h; ow = p.in_w; oy = y; ox = x; }
             const int64_t opix = ((int64_t)n * oh + oy) * ow + ox;
-            // narrow fp32 skip source (raw input channels of lu0.conv2): its 3x3 neighbourhood in registers
-            float xs[9 * (SKIPC > 0 ? SKIPC : 1)];
+            // narrow fp32 source (raw input channels of lu0.conv2 / the legacy 1x1 shortcut): its taps in registers
+            float xs[(SKT > 0 ? SKT : 1) * (SKIPC > 0 ? SKIPC : 1)];
             if (SKIPC > 0) {
 #pragma unroll
-                for (int tp = 0; tp < 9; ++tp) {
-                    const TcTap tap = p.taps[0][tp];
+                for (int tp = 0; tp < SKT; ++tp) {
+                    const TcTap tap = p.skip_taps[tp];
                     const int yy = y + tap.dy, xx = x + tap.dx;
                     const bool inb = valid && yy >= 0 && yy < p.in_h && xx >= 0 && xx < p.in_w;
 #pragma unroll
@@ -471,12 +477,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 }
                 if (SKIPC > 0) {
 #pragma unroll
-                    for (int tp = 0; tp < 9; ++tp) {
-                        const int wi = p.taps[0][tp].wi;
+                    for (int tp = 0; tp < SKT; ++tp) {
 #pragma unroll
                         for (int cs = 0; cs < SKIPC; ++cs) {
                             const float xv = xs[tp * SKIPC + cs];
-                            const float4* w4 = reinterpret_cast<const float4*>(s_skipw + (wi * SKIPC + cs) * cpad + co);
+                            const float4* w4 = reinterpret_cast<const float4*>(s_skipw + (tp * SKIPC + cs) * cpad + co);
 #pragma unroll
                             for (int j4 = 0; j4 < 4; ++j4) {
                                 const float4 w = w4[j4];
@@ -488,6 +493,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = act_fn(v[j], p.act, p.leaky);
+                if (p.post_scale) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (co + j < p.cout) v[j] = fmaf(v[j], __ldg(p.post_scale + co + j), __ldg(p.post_shift + co + j));
+                }
                 if (p.top_w) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
@@ -580,7 +590,7 @@ EncodeTiledFn encode_fn() {
 
 size_t tc_conv_fixed_bytes(const TcConvParams& p) {
     const size_t cpad = (size_t)p.n_ntiles * p.n_t;
-    const size_t tables = ((size_t)9 * p.skip_c * cpad + (p.top_w ? cpad * p.top_k + 4 : 0)) * sizeof(float);
+    const size_t tables = ((size_t)(p.skip_src ? p.skip_ntaps : 0) * p.skip_c * cpad + (p.top_w ? cpad * p.top_k + 4 : 0)) * sizeof(float);
     return (2 * (size_t)(p.stages + (p.halo ? p.b_stages : 0)) + 4) * 8 + 16 + tables + 1024;
 }
 size_t tc_conv_a_bytes(const TcConvParams& p) {
@@ -593,28 +603,30 @@ size_t tc_conv_smem_bytes(const TcConvParams& p) {
     return p.stages * (size_t)(p.kslab > 0 ? p.kslab : 1) * (tc_conv_a_bytes(p) + tc_conv_b_bytes(p)) + tc_conv_fixed_bytes(p);
 }
 
-template <int SKIPC, bool PAIR, bool HALO>
+template <int SKIPC, int SKT, bool PAIR, bool HALO>
 static cudaError_t configure_one() {
-    return cudaFuncSetAttribute(tc_conv_kernel<SKIPC, PAIR, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return cudaFuncSetAttribute(tc_conv_kernel<SKIPC, SKT, PAIR, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
-template <int SKIPC>
-static cudaError_t configure_skipc() {
-    cudaError_t e = configure_one<SKIPC, false, false>();
-    if (e == cudaSuccess) e = configure_one<SKIPC, true, false>();
-    if (e == cudaSuccess) e = configure_one<SKIPC, false, true>();
-    if (e == cudaSuccess) e = configure_one<SKIPC, true, true>();
+template <int SKIPC, int SKT>
+static cudaError_t configure_skip() {
+    cudaError_t e = configure_one<SKIPC, SKT, false, false>();
+    if (e == cudaSuccess) e = configure_one<SKIPC, SKT, true, false>();
+    if (e == cudaSuccess) e = configure_one<SKIPC, SKT, false, true>();
+    if (e == cudaSuccess) e = configure_one<SKIPC, SKT, true, true>();
     return e;
 }
 
 cudaError_t tc_conv_configure() {
-    cudaError_t e = configure_skipc<0>();
-    if (e == cudaSuccess) e = configure_skipc<1>();
-    if (e == cudaSuccess) e = configure_skipc<2>();
+    cudaError_t e = configure_skip<0, 0>();
+    if (e == cudaSuccess) e = configure_skip<1, 1>();
+    if (e == cudaSuccess) e = configure_skip<1, 9>();
+    if (e == cudaSuccess) e = configure_skip<2, 9>();
+    if (e == cudaSuccess) e = configure_skip<1, 25>();
     return e;
 }
 
-template <int SKIPC, bool PAIR, bool HALO>
+template <int SKIPC, int SKT, bool PAIR, bool HALO>
 static cudaError_t launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcConvParams& p,
                               int grid, size_t smem, cudaStream_t s) {
     cudaLaunchConfig_t cfg = {};
@@ -623,14 +635,14 @@ static cudaError_t launch_one(const CUtensorMap& a0, const CUtensorMap& a1, cons
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, tc_conv_kernel<SKIPC, PAIR, HALO>, a0, a1, b, p);
+    return cudaLaunchKernelEx(&cfg, tc_conv_kernel<SKIPC, SKT, PAIR, HALO>, a0, a1, b, p);
 }
 
-template <int SKIPC>
-static cudaError_t launch_skipc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcConvParams& p,
-                                int grid, size_t smem, cudaStream_t s) {
-    if (p.pair) return p.halo ? launch_one<SKIPC, true, true>(a0, a1, b, p, grid, smem, s) : launch_one<SKIPC, true, false>(a0, a1, b, p, grid, smem, s);
-    return p.halo ? launch_one<SKIPC, false, true>(a0, a1, b, p, grid, smem, s) : launch_one<SKIPC, false, false>(a0, a1, b, p, grid, smem, s);
+template <int SKIPC, int SKT>
+static cudaError_t launch_skip(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcConvParams& p,
+                               int grid, size_t smem, cudaStream_t s) {
+    if (p.pair) return p.halo ? launch_one<SKIPC, SKT, true, true>(a0, a1, b, p, grid, smem, s) : launch_one<SKIPC, SKT, true, false>(a0, a1, b, p, grid, smem, s);
+    return p.halo ? launch_one<SKIPC, SKT, false, true>(a0, a1, b, p, grid, smem, s) : launch_one<SKIPC, SKT, false, false>(a0, a1, b, p, grid, smem, s);
 }
 
 cudaError_t launch_tc_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcConvParams& p,
@@ -645,10 +657,12 @@ cudaError_t launch_tc_conv(const CUtensorMap& a0, const CUtensorMap& a1, const C
     size_t smem = tc_conv_smem_bytes(p);
     if (smem < 120 * 1024) smem = 120 * 1024;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    const int skipc = p.skip_src ? p.skip_c : 0;
-    if (skipc == 0) return launch_skipc<0>(a0, a1, b, p, grid, smem, s);
-    if (skipc == 1) return launch_skipc<1>(a0, a1, b, p, grid, smem, s);
-    if (skipc == 2) return launch_skipc<2>(a0, a1, b, p, grid, smem, s);
+    const int skipc = p.skip_src ? p.skip_c : 0, skt = p.skip_src ? p.skip_ntaps : 0;
+    if (skipc == 0) return launch_skip<0, 0>(a0, a1, b, p, grid, smem, s);
+    if (skipc == 1 && skt == 1) return launch_skip<1, 1>(a0, a1, b, p, grid, smem, s);
+    if (skipc == 1 && skt == 9) return launch_skip<1, 9>(a0, a1, b, p, grid, smem, s);
+    if (skipc == 2 && skt == 9) return launch_skip<2, 9>(a0, a1, b, p, grid, smem, s);
+    if (skipc == 1 && skt == 25) return launch_skip<1, 25>(a0, a1, b, p, grid, smem, s);
     return cudaErrorInvalidValue;
 }
 

@@ -314,24 +314,38 @@ int build_plan(umx_handle* h) {
     return UMX_OK;
 }
 
-// lu0.conv2 pattern: concat(raw input with <= 2 channels, wide up tensor) -> the wide part runs on the
-// tensor cores, the narrow part is a handful of fp32 FMAs per output in the epilogue.
-bool tc_skip_mode(const umx_handle* h, const Op& op) {
-    const ConvSpec& sp = op.spec;
-    if (sp.terms.size() != 1 || sp.terms[0].src1 < 0 || sp.transpose || sp.pool) return false;
-    const Buffer& a = h->bufs[sp.terms[0].src0];
-    const Buffer& b = h->bufs[sp.terms[0].src1];
-    return a.c <= 2 && b.c >= 8;
+enum { TC_NONE = 0, TC_PLAIN = 1, TC_SKIP_CONCAT = 2, TC_SHORT_SKIP = 3, TC_SHORT_A1 = 4 };
+
+bool skip_combo_ok(int c, int ntaps) {       // (channels, taps) combinations instantiated in kernels_tc.cu
+    return (c == 1 && (ntaps == 1 || ntaps == 9 || ntaps == 25)) || (c == 2 && ntaps == 9);
 }
 
-bool tc_eligible(const umx_handle* h, const Op& op) {
-    if (h->precision == UMX_PREC_FP32 || op.kind != OP_CONV) return false;
+// Which tensor-path form (if any) can run this op.
+//  - lu0.conv2 pattern: concat(raw input with <= 2 channels, wide up tensor): the wide part runs on the tensor
+//    cores, the narrow part is a handful of fp32 FMAs per output in the epilogue (TC_SKIP_CONCAT)
+//  - legacy down layer: k x k conv of the chain + 1x1 shortcut of the layer input (UnMicst.py:91-99): the shortcut
+//    is either folded into the epilogue (1-channel input, TC_SHORT_SKIP) or joins the K loop at the centre tap
+int tc_mode_of(const umx_handle* h, const Op& op) {
+    if (h->precision == UMX_PREC_FP32 || op.kind != OP_CONV) return TC_NONE;
     const ConvSpec& sp = op.spec;
-    if (sp.terms.size() != 1 || sp.has_post || sp.terms[0].k != 3) return false;
-    const Buffer& a = h->bufs[sp.terms[0].src0];
-    if (a.h < 4 || a.w < 4) return false;
-    if (tc_skip_mode(h, op)) return true;
-    return a.c >= 8;        // narrower inputs (the raw image) stay on the CUDA cores
+    const TermHost& T0 = sp.terms[0];
+    if (T0.k != 3 && T0.k != 5) return TC_NONE;
+    if (sp.transpose && sp.terms.size() != 1) return TC_NONE;
+    const Buffer& a = h->bufs[T0.src0];
+    if (a.h < 4 || a.w < 4) return TC_NONE;
+    if (sp.terms.size() == 1) {
+        if (T0.src1 >= 0 && a.c <= 2 && !sp.transpose && !sp.pool && h->bufs[T0.src1].c >= 8 && skip_combo_ok(a.c, T0.k * T0.k))
+            return TC_SKIP_CONCAT;
+        return a.c >= 8 ? TC_PLAIN : TC_NONE;
+    }
+    if (sp.terms.size() == 2) {
+        const TermHost& T1 = sp.terms[1];
+        if (T1.k != 1 || T1.src1 >= 0 || T0.src1 >= 0 || a.c < 8) return TC_NONE;
+        const Buffer& sc = h->bufs[T1.src0];
+        if (sc.c >= 8) return TC_SHORT_A1;
+        return skip_combo_ok(sc.c, 1) ? TC_SHORT_SKIP : TC_NONE;
+    }
+    return TC_NONE;
 }
 
 int pick_n_tile(int cout) {
@@ -418,16 +432,22 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     TcConvParams& tp = op.tcp;
     memset(&tp, 0, sizeof(tp));
     const TermHost& T = sp.terms[0];
-    const Buffer& a0 = h->bufs[op.skip_mode ? T.src1 : T.src0];
-    const Buffer* a1 = (!op.skip_mode && T.src1 >= 0) ? &h->bufs[T.src1] : nullptr;
+    const int mode = op.tc_mode, k = T.k, ntaps_w = k * k;
+    const Buffer& a0 = h->bufs[mode == TC_SKIP_CONCAT ? T.src1 : T.src0];
+    const Buffer* a1 = nullptr;
+    if (mode == TC_PLAIN && T.src1 >= 0) a1 = &h->bufs[T.src1];
+    if (mode == TC_SHORT_A1) a1 = &h->bufs[sp.terms[1].src0];
+    const Buffer* narrow = mode == TC_SKIP_CONCAT ? &h->bufs[T.src0] : (mode == TC_SHORT_SKIP ? &h->bufs[sp.terms[1].src0] : nullptr);
     const int planes = h->precision == UMX_PREC_SINGLE ? 1 : 2;
     tp.in_h = a0.h; tp.in_w = a0.w;
     tp.bw = std::min(a0.w, 16); tp.bh = std::min(a0.h, 128 / tp.bw); tp.bn = 128 / (tp.bw * tp.bh);
     tp.c0 = a0.cs(); tp.c1 = a1 ? a1->cs() : 0;          // storage channels (zero-padded to a multiple of 8)
     tp.cout = sp.cout; tp.n_t = pick_n_tile(sp.cout); tp.n_ntiles = (sp.cout + tp.n_t - 1) / tp.n_t;
     tp.nphase = sp.transpose ? 4 : 1; tp.os = sp.transpose ? 2 : 1;
+    tp.a1_center = mode == TC_SHORT_A1 ? 1 : 0;
+    tp.center_tap = ntaps_w / 2;
     ConvTerm tt; memset(&tt, 0, sizeof(tt));
-    if (sp.transpose) convt_taps(&tt, 3); else conv_taps(&tt, 3);
+    if (sp.transpose) convt_taps(&tt, k); else conv_taps(&tt, k);
     for (int ph = 0; ph < tp.nphase; ++ph) {
         tp.ntaps[ph] = tt.ntaps[ph];
         for (int i = 0; i < tt.ntaps[ph]; ++i) tp.taps[ph][i] = TcTap{tt.dy[ph][i], tt.dx[ph][i], tt.wi[ph][i], 0};
@@ -435,10 +455,10 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     tp.planes = planes;
     {
         const char* e = getenv("UMX_TC_PAIR");
-        tp.pair = (e ? atoi(e) : 1) && (tp.n_t % 32 == 0 || tp.n_t % 16 == 0) && ((tp.n_t / 2) % 8 == 0) ? 1 : 0;
+        tp.pair = (e ? atoi(e) : 1) && ((tp.n_t / 2) % 8 == 0) ? 1 : 0;
     }
     // halo mode for the high-resolution layers: A is fetched once per 64-channel slab as a pixel patch
-    // (instead of once per tap), cutting the L2->SM traffic of A by ~6x
+    // (instead of once per tap), cutting the L2->SM traffic of A by ~k*k/1.4
     {
         const char* e = getenv("UMX_TC_HALO");
         if ((e ? atoi(e) : 1) && a0.w >= 16 && a0.h >= 16) {
@@ -447,24 +467,27 @@ int lower_conv_tc(umx_handle* h, Op& op) {
             tp.pw = tp.bw + tt.hx0 + tt.hx1; tp.ph = tp.bh + tt.hy0 + tt.hy1;
         }
     }
+    const int skip_c = narrow ? narrow->c : 0;
+    const int skip_nt = mode == TC_SKIP_CONCAT ? ntaps_w : (mode == TC_SHORT_SKIP ? 1 : 0);
     {
         const size_t cpad = (size_t)tp.n_ntiles * tp.n_t;
-        const size_t tables = (op.skip_mode ? (size_t)9 * h->bufs[T.src0].c * cpad * 4 : 0) + (op.fuse_top >= 0 ? (cpad * h->K + 8) * 4 : 0);
+        const size_t tables = (size_t)skip_nt * skip_c * cpad * 4 + (op.fuse_top >= 0 ? (cpad * h->K + 8) * 4 : 0);
         const size_t budget = 227 * 1024 - 2048 - 512 - tables;
-        const size_t ab = tc_conv_a_bytes(tp), bb = tc_conv_b_bytes(tp);
+        const size_t bb = tc_conv_b_bytes(tp);
         if (tp.halo) {
+            const size_t ab = tc_conv_a_bytes(tp);
             tp.stages = 2;
             tp.gb = 3;
             if (const char* e = getenv("UMX_TC_GB")) tp.gb = std::max(1, std::min(9, atoi(e)));
             while (tp.gb > 1 && budget < 2 * ab + 2 * (size_t)tp.gb * bb) tp.gb--;
-            tp.b_stages = (int)std::min<size_t>(6, (budget - 2 * ab) / ((size_t)tp.gb * bb));
+            tp.b_stages = budget > 2 * ab ? (int)std::min<size_t>(6, (budget - 2 * ab) / ((size_t)tp.gb * bb)) : 0;
             if (tp.b_stages < 2) { tp.halo = 0; tp.bw = std::min(a0.w, 16); tp.bh = std::min(a0.h, 128 / tp.bw); tp.bn = 128 / (tp.bw * tp.bh); }
         }
         tp.kslab = 1;
         if (!tp.halo) {
             // single precision issues one MMA per K step: put two slabs behind each barrier round trip
-            const int n_chunks = (tp.c0 + 63) / 64 + (tp.c1 + 63) / 64;
-            tp.kslab = std::min(planes == 1 ? 2 : 1, n_chunks);
+            const int n_chunks = (tp.c0 + 63) / 64 + (tp.a1_center ? 0 : (tp.c1 + 63) / 64);
+            tp.kslab = std::min(planes == 1 ? 2 : 1, std::max(1, n_chunks));
             if (const char* e = getenv("UMX_TC_KSLAB")) tp.kslab = std::max(1, std::min(std::min(4, n_chunks), atoi(e)));
             while (tp.kslab > 1 && budget / (tp.kslab * (tc_conv_a_bytes(tp) + bb)) < 3) tp.kslab--;
             tp.stages = (int)std::min<size_t>(6, budget / (tp.kslab * (tc_conv_a_bytes(tp) + bb)));
@@ -479,35 +502,48 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     tp.act = sp.act; tp.leaky = kLeaky; tp.pool = sp.pool ? 1 : 0;
     float* d = nullptr;
     if (sp.has_bias) { UMX_TRY(upload(h, sp.bias, &d)); tp.bias = d; }
+    if (sp.has_post) {
+        UMX_TRY(upload(h, sp.post_scale, &d)); tp.post_scale = d;
+        UMX_TRY(upload(h, sp.post_shift, &d)); tp.post_shift = d;
+    }
     const Buffer& ob = h->bufs[op.out_buf];
     tp.out_f = ob.d; tp.out_h = ob.dh; tp.out_planes = ob.planes; tp.out_plane_elems = ob.plane_elems; tp.out_cs = ob.cs();
     // weights -> fp16 planes on the device; input-channel rows follow the padded storage layout [c0s | c1s]
     const int cin = tp.c0 + tp.c1;
-    std::vector<float> wmain;
-    if (!op.skip_mode) {
+    std::vector<float> wmain((size_t)ntaps_w * cin * sp.cout, 0.f);
+    auto put_rows = [&](const std::vector<float>& w, int w_taps, int w_cin, int row0, int nrows, int dst0, int tap_dst0) {
+        for (int t = 0; t < w_taps; ++t)
+            for (int i = 0; i < nrows; ++i)
+                memcpy(&wmain[((size_t)(tap_dst0 + t) * cin + dst0 + i) * sp.cout], &w[((size_t)t * w_cin + row0 + i) * sp.cout],
+                       sp.cout * sizeof(float));
+    };
+    if (mode == TC_PLAIN) {
         const int r0 = a0.c, r1 = a1 ? a1->c : 0;
-        wmain.assign((size_t)9 * cin * sp.cout, 0.f);
-        for (int t = 0; t < 9; ++t)
-            for (int i = 0; i < r0 + r1; ++i) {
-                const int dst = i < r0 ? i : tp.c0 + (i - r0);
-                memcpy(&wmain[((size_t)t * cin + dst) * sp.cout], &T.w[((size_t)t * (r0 + r1) + i) * sp.cout], sp.cout * sizeof(float));
-            }
+        put_rows(T.w, ntaps_w, r0 + r1, 0, r0, 0, 0);
+        if (r1) put_rows(T.w, ntaps_w, r0 + r1, r0, r1, tp.c0, 0);
+    } else if (mode == TC_SKIP_CONCAT) {
+        put_rows(T.w, ntaps_w, skip_c + a0.c, skip_c, a0.c, 0, 0);
+    } else if (mode == TC_SHORT_SKIP) {
+        put_rows(T.w, ntaps_w, a0.c, 0, a0.c, 0, 0);
+    } else {    // TC_SHORT_A1: the 1x1 shortcut's rows live at the centre tap only
+        put_rows(T.w, ntaps_w, a0.c, 0, a0.c, 0, 0);
+        put_rows(sp.terms[1].w, 1, a1->c, 0, a1->c, tp.c0, tp.center_tap);
     }
-    if (op.skip_mode) {
-        const Buffer& sk = h->bufs[T.src0];
-        const int cs = sk.c, ctot = cs + a0.c;
-        std::vector<float> wskip((size_t)9 * cs * sp.cout);
-        wmain.assign((size_t)9 * cin * sp.cout, 0.f);
-        for (int t = 0; t < 9; ++t)
-            for (int i = 0; i < ctot; ++i)
-                for (int o = 0; o < sp.cout; ++o) {
-                    const float v = T.w[((size_t)t * ctot + i) * sp.cout + o];
-                    if (i < cs) wskip[((size_t)t * cs + i) * sp.cout + o] = v;
-                    else wmain[((size_t)t * cin + (i - cs)) * sp.cout + o] = v;
-                }
+    if (narrow) {
+        std::vector<float> wskip((size_t)skip_nt * skip_c * sp.cout);
+        if (mode == TC_SKIP_CONCAT) {
+            const int ctot = skip_c + a0.c;
+            for (int t = 0; t < ntaps_w; ++t)
+                for (int i = 0; i < skip_c; ++i)
+                    memcpy(&wskip[((size_t)t * skip_c + i) * sp.cout], &T.w[((size_t)t * ctot + i) * sp.cout], sp.cout * sizeof(float));
+            for (int t = 0; t < ntaps_w; ++t) tp.skip_taps[t] = tp.taps[0][t];
+        } else {
+            wskip = sp.terms[1].w;
+            tp.skip_taps[0] = TcTap{0, 0, 0, 0};
+        }
         UMX_TRY(upload(h, wskip, &d));
-        tp.skip_w = d; tp.skip_c = cs; tp.skip_src = sk.d;
-        if (!sk.d) { set_error("%s: fp32 skip source missing", op.name.c_str()); return UMX_EINVAL; }
+        tp.skip_w = d; tp.skip_c = skip_c; tp.skip_ntaps = skip_nt; tp.skip_src = narrow->d;
+        if (!narrow->d) { set_error("%s: fp32 skip source missing", op.name.c_str()); return UMX_EINVAL; }
     }
     if (op.fuse_top >= 0) {
         Op& top = h->ops[op.fuse_top];
@@ -516,12 +552,12 @@ int lower_conv_tc(umx_handle* h, Op& op) {
         tp.top_k = h->K;
     }
     std::vector<__half> wh;
-    split_weights(wmain, 9, cin, sp.cout, planes, &wh);
+    split_weights(wmain, ntaps_w, cin, sp.cout, planes, &wh);
     __half* dw = nullptr;
     UMX_CUDA_TRY(cudaMalloc(&dw, wh.size() * sizeof(__half)));
     h->dev_allocs.push_back(reinterpret_cast<float*>(dw));
     UMX_CUDA_TRY(cudaMemcpy(dw, wh.data(), wh.size() * sizeof(__half), cudaMemcpyHostToDevice));
-    int rc = make_weight_tensor_map(&op.mapB, dw, planes, 9, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, planes);
+    int rc = make_weight_tensor_map(&op.mapB, dw, planes, ntaps_w, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, planes);
     if (rc) { set_error("%s: cuTensorMapEncodeTiled(weights) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
     if (!a0.dh || (a1 && !a1->dh)) { set_error("%s: fp16 source buffer missing", op.name.c_str()); return UMX_EINVAL; }
     const int box_w = tp.halo ? tp.pw : tp.bw, box_h = tp.halo ? tp.ph : tp.bh, box_p = tp.halo ? 1 : planes;
@@ -541,8 +577,9 @@ int lower_conv_tc(umx_handle* h, Op& op) {
 int lower_plan(umx_handle* h) {
     for (size_t i = 0; i < h->ops.size(); ++i) {
         Op& op = h->ops[i];
-        op.use_tc = tc_eligible(h, op);
-        op.skip_mode = op.use_tc && tc_skip_mode(h, op);
+        op.tc_mode = tc_mode_of(h, op);
+        op.use_tc = op.tc_mode != TC_NONE;
+        op.skip_mode = op.tc_mode == TC_SKIP_CONCAT;
         op.use_first = !op.use_tc && first_eligible(h, op);
     }
     // lt 1x1 conv + softmax rides in the epilogue of the conv that feeds it when one CTA tile spans all channels
@@ -561,8 +598,10 @@ int lower_plan(umx_handle* h) {
     }
     for (auto& op : h->ops) {
         if (op.kind == OP_CONV) {
-            for (auto& t : op.spec.terms) {
-                if (op.skip_mode) { h->bufs[t.src0].need_f = true; h->bufs[t.src1].need_h = true; continue; }
+            for (size_t ti = 0; ti < op.spec.terms.size(); ++ti) {
+                const TermHost& t = op.spec.terms[ti];
+                if (op.tc_mode == TC_SKIP_CONCAT) { h->bufs[t.src0].need_f = true; h->bufs[t.src1].need_h = true; continue; }
+                if (op.tc_mode == TC_SHORT_SKIP && ti == 1) { h->bufs[t.src0].need_f = true; continue; }
                 for (int s : {t.src0, t.src1}) {
                     if (s < 0) continue;
                     if (op.use_tc) h->bufs[s].need_h = true; else h->bufs[s].need_f = true;

@@ -75,7 +75,11 @@ struct Op {
     bool use_tc = false;
     bool use_first = false;          // dedicated first-layer kernel (1-2 input channels, 3x3, pooled)
     FirstParams fp{};
-    bool skip_mode = false;          // tensor path with the narrow first concat source folded into the epilogue
+    // how the tensor path maps the op: 1 plain (one or two wide concat sources), 2 narrow first concat source folded
+    // into the epilogue, 3 two terms with a narrow 1x1 shortcut in the epilogue, 4 two terms with a wide 1x1
+    // shortcut joining the K loop at the centre tap
+    int tc_mode = 0;
+    bool skip_mode = false;          // tc_mode == 2
     int fuse_top = -1;               // index of the OP_TOP fused into this conv's epilogue
     bool fused_away = false;         // OP_TOP executed inside the preceding conv
     ConvParams cp{};                 // fp32 CUDA-core implementation

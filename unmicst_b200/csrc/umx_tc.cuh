@@ -19,7 +19,7 @@ struct TcConvParams {
     int32_t n_ntiles;            // ceil(cout / n_t)
     int32_t nphase, os;          // conv: 1,1   conv-transpose: 4,2
     int32_t ntaps[4];
-    TcTap   taps[4][9];
+    TcTap   taps[4][25];         // per phase: input offset and weight tap (conv 3x3/5x5: 1 phase; conv-transpose: 4 phases, <= 9 taps)
     int32_t planes;              // 1: fp16 operands, 1 MMA/product; 2: hi/lo split, 3 MMAs/product
     int32_t stages;              // smem pipeline depth (halo mode: patch slots)
     int32_t halo;                // 1: one (bh+halo) x (bw+halo) pixel patch per 64-channel slab serves every tap
@@ -31,7 +31,11 @@ struct TcConvParams {
     int32_t act;                 // umx::Act
     float   leaky;
     int32_t pool;                // fused 2x2 max-pool (conv only)
+    int32_t a1_center;           // 1: the second source is a 1x1 shortcut: its slabs join the K loop at the centre tap only
+    int32_t center_tap;          // index of the (0,0) tap in taps[0]
     const float* bias;           // [cout] or nullptr
+    const float* post_scale;     // [cout] affine applied after the activation (legacy: batch-norm follows the ReLU) or nullptr
+    const float* post_shift;
     __half* out_h;               // fp16 plane(s) [planes][n][oh][ow][cout] or nullptr
     int64_t out_plane_elems;     // elements between the hi and lo plane
     int32_t out_planes;          // planes to write into out_h (1 or 2)
@@ -39,8 +43,10 @@ struct TcConvParams {
     float*  out_f;               // fp32 [n][oh][ow][cout] or nullptr
     // narrow skip source handled in fp32 in the epilogue (raw input channels of lu0.conv2)
     const float* skip_src;       // [n][in_h][in_w][skip_c] or nullptr
-    const float* skip_w;         // [9][skip_c][cout] fp32 (BN scale folded)
+    const float* skip_w;         // [skip_ntaps][skip_c][cout] fp32 (BN scale folded)
     int32_t skip_c;
+    int32_t skip_ntaps;          // 1 (1x1 shortcut), 9 or 25 (k x k taps of a concat source)
+    TcTap   skip_taps[25];
     // fused lt 1x1 conv + softmax (replaces the activation store when top_w != nullptr)
     const float* top_w;          // [cout][K]
     const float* top_b;          // [K] or nullptr
