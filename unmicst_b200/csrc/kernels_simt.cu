@@ -218,51 +218,56 @@ __global__ void __launch_bounds__(NTHR) conv_simt_kernel(const __grid_constant__
     }
 }
 
-// Block: one 32x32-pixel region of one tile (16x16 pooled pixels); thread: one pooled pixel, all
-// output channels in groups of 16.  Weights are read from shared memory as warp-wide broadcasts.
-template <int CIN>
+// First layer: k x k SAME conv from 1 or 2 input channels (+ bias, activation, optional 2x2 max-pool).
+// Block: one 32x32-pixel region of one tile; thread: one 2x2 pixel block, all output channels in groups of 16.
+// Weights are read from shared memory as warp-wide broadcasts (padded to a multiple of 16 channels with zeros).
+template <int CIN, int KS>
 __global__ void __launch_bounds__(256) first_conv_kernel(const FirstParams p) {
+    constexpr int R = KS / 2, PW = 32 + 2 * R, NB = 2 + 2 * R;
     extern __shared__ __align__(16) float smem[];
-    float* xin = smem;                                   // [34][34][CIN]
-    float* ws = smem + ((34 * 34 * CIN + 3) & ~3);       // [9][CIN][cout]
-    float* bs = ws + 9 * CIN * p.cout;                   // [cout]
+    const int cpad = (p.cout + 15) & ~15;
+    float* xin = smem;                                   // [PW][PW][CIN]
+    float* ws = smem + ((PW * PW * CIN + 3) & ~3);       // [KS*KS][CIN][cpad]
+    float* bs = ws + KS * KS * CIN * cpad;               // [cpad]
     const int nb = p.S / 32;
     const int n = blockIdx.x / (nb * nb);
     const int rb = blockIdx.x % (nb * nb);
     const int y0 = (rb / nb) * 32, x0 = (rb % nb) * 32;
-    for (int i = threadIdx.x; i < 34 * 34; i += 256) {
-        const int r = i / 34, c = i % 34;
-        const int gy = y0 + r - 1, gx = x0 + c - 1;
+    for (int i = threadIdx.x; i < PW * PW; i += 256) {
+        const int r = i / PW, c = i % PW;
+        const int gy = y0 + r - R, gx = x0 + c - R;
         const bool inb = gy >= 0 && gy < p.S && gx >= 0 && gx < p.S;
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci)
             xin[i * CIN + ci] = inb ? __ldg(p.src + (((int64_t)n * p.S + gy) * p.S + gx) * CIN + ci) : 0.f;
     }
-    for (int i = threadIdx.x; i < 9 * CIN * p.cout; i += 256) ws[i] = __ldg(p.w + i);
-    for (int i = threadIdx.x; i < p.cout; i += 256) bs[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+    for (int i = threadIdx.x; i < KS * KS * CIN * cpad; i += 256) {
+        const int c = i % cpad;
+        ws[i] = c < p.cout ? __ldg(p.w + (size_t)(i / cpad) * p.cout + c) : 0.f;
+    }
+    for (int i = threadIdx.x; i < cpad; i += 256) bs[i] = (p.bias && i < p.cout) ? __ldg(p.bias + i) : 0.f;
     __syncthreads();
     const int py = threadIdx.x >> 4, px = threadIdx.x & 15;
-    float in[4][4][CIN];
+    float in[NB][NB][CIN];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < NB; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
+        for (int b = 0; b < NB; ++b)
 #pragma unroll
-            for (int ci = 0; ci < CIN; ++ci) in[a][b][ci] = xin[((2 * py + a) * 34 + 2 * px + b) * CIN + ci];
-    const int oh = p.S / 2;
-    const int64_t opix = ((int64_t)n * oh + (y0 / 2 + py)) * oh + (x0 / 2 + px);
-    for (int cg = 0; cg < p.cout; cg += 16) {
+            for (int ci = 0; ci < CIN; ++ci) in[a][b][ci] = xin[((2 * py + a) * PW + 2 * px + b) * CIN + ci];
+    const int oh = p.pool ? p.S / 2 : p.S;
+    for (int cg = 0; cg < cpad; cg += 16) {
         float acc[4][16];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[q][j] = bs[cg + j];
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3, dx = tap % 3;
+        for (int tap = 0; tap < KS * KS; ++tap) {
+            const int dy = tap / KS, dx = tap % KS;
 #pragma unroll
             for (int ci = 0; ci < CIN; ++ci) {
-                const float4* w4 = reinterpret_cast<const float4*>(ws + (tap * CIN + ci) * p.cout + cg);
+                const float4* w4 = reinterpret_cast<const float4*>(ws + (tap * CIN + ci) * cpad + cg);
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
                     const float4 w = w4[j4];
@@ -277,20 +282,38 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const FirstParams p) {
                 }
             }
         }
-        float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-            v[j] = fmaxf(fmaxf(apply_act(acc[0][j], p.act, p.leaky), apply_act(acc[1][j], p.act, p.leaky)),
-                         fmaxf(apply_act(acc[2][j], p.act, p.leaky), apply_act(acc[3][j], p.act, p.leaky)));
-        const int64_t oo = opix * p.cout + cg;
-        if (p.out) {
+        for (int q = 0; q < 4; ++q)
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4)
-                reinterpret_cast<float4*>(p.out + oo)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+            for (int j = 0; j < 16; ++j) acc[q][j] = apply_act(acc[q][j], p.act, p.leaky);
+        const int nq = p.pool ? 1 : 4;
+        if (p.pool) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[0][j] = fmaxf(fmaxf(acc[0][j], acc[1][j]), fmaxf(acc[2][j], acc[3][j]));
         }
-        if (p.out_h) {
+        for (int q = 0; q < nq; ++q) {
+            const int oy = p.pool ? (y0 / 2 + py) : (y0 + 2 * py + (q >> 1));
+            const int ox = p.pool ? (x0 / 2 + px) : (x0 + 2 * px + (q & 1));
+            const int64_t opix = ((int64_t)n * oh + oy) * oh + ox;
+            float v[16];
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) store_h2x4(p.out_h + oo + j4 * 4, p.out_plane_elems, p.out_planes, v + j4 * 4);
+            for (int j = 0; j < 16; ++j) v[j] = q == 0 ? acc[0][j] : (q == 1 ? acc[1][j] : (q == 2 ? acc[2][j] : acc[3][j]));
+            if (p.out) {
+                float* o = p.out + opix * p.cout + cg;
+                if (cg + 16 <= p.cout && !(p.cout & 3)) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4)
+                        reinterpret_cast<float4*>(o)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (cg + j < p.cout) o[j] = v[j];
+                }
+            }
+            if (p.out_h) {
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4)
+                    if (cg + j4 * 4 < p.out_cs) store_h2x4(p.out_h + opix * p.out_cs + cg + j4 * 4, p.out_plane_elems, p.out_planes, v + j4 * 4);
+            }
         }
     }
 }
@@ -466,15 +489,33 @@ cudaError_t launch_top_softmax(const TopParams& p, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+size_t first_conv_smem_bytes(int cin, int ks, int cout) {
+    const int pw = 32 + 2 * (ks / 2), cpad = (cout + 15) & ~15;
+    return (((size_t)pw * pw * cin + 3) & ~(size_t)3) * 4 + ((size_t)ks * ks * cin * cpad + cpad) * 4;
+}
+
+template <int CIN, int KS>
+static cudaError_t launch_first(const FirstParams& p, unsigned grid, size_t sm, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(first_conv_kernel<CIN, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    first_conv_kernel<CIN, KS><<<grid, 256, sm, s>>>(p);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_first_conv(const FirstParams& p, cudaStream_t s) {
     if (p.n_tiles == 0) return cudaSuccess;
     const int nb = p.S / 32;
     const unsigned grid = (unsigned)p.n_tiles * nb * nb;
-    const size_t sm = (((size_t)34 * 34 * p.cin + 3) & ~(size_t)3) * 4 + ((size_t)9 * p.cin * p.cout + p.cout) * 4;
-    if (p.cin == 1) first_conv_kernel<1><<<grid, 256, sm, s>>>(p);
-    else if (p.cin == 2) first_conv_kernel<2><<<grid, 256, sm, s>>>(p);
-    else return cudaErrorInvalidValue;
-    return cudaGetLastError();
+    const size_t sm = first_conv_smem_bytes(p.cin, p.ks, p.cout);
+    if (p.cin == 1 && p.ks == 3) return launch_first<1, 3>(p, grid, sm, s);
+    if (p.cin == 2 && p.ks == 3) return launch_first<2, 3>(p, grid, sm, s);
+    if (p.cin == 1 && p.ks == 5) return launch_first<1, 5>(p, grid, sm, s);
+    if (p.cin == 2 && p.ks == 5) return launch_first<2, 5>(p, grid, sm, s);
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_gather_tiles(const GatherParams& p, cudaStream_t s) {

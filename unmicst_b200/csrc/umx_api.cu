@@ -407,9 +407,11 @@ int lower_conv_simt(umx_handle* h, Op& op) {
 bool first_eligible(const umx_handle* h, const Op& op) {
     if (op.kind != OP_CONV) return false;
     const ConvSpec& sp = op.spec;
-    if (sp.terms.size() != 1 || sp.has_post || sp.terms[0].k != 3 || sp.terms[0].src1 >= 0 || sp.transpose || !sp.pool) return false;
+    if (sp.terms.size() != 1 || sp.has_post || sp.terms[0].src1 >= 0 || sp.transpose) return false;
+    const int k = sp.terms[0].k;
+    if (k != 3 && k != 5) return false;
     const Buffer& a = h->bufs[sp.terms[0].src0];
-    return a.c <= 2 && sp.cout % 16 == 0 && a.h % 32 == 0 && a.h == a.w && (9 * a.c * sp.cout + sp.cout + 34 * 34 * a.c + 4) * 4 <= 48 * 1024;
+    return a.c <= 2 && a.h % 32 == 0 && a.h == a.w && first_conv_smem_bytes(a.c, k, sp.cout) <= 96 * 1024;
 }
 
 int lower_conv_first(umx_handle* h, Op& op) {
@@ -419,11 +421,12 @@ int lower_conv_first(umx_handle* h, Op& op) {
     const Buffer& a = h->bufs[sp.terms[0].src0];
     if (!a.d) { set_error("%s: fp32 source buffer missing", op.name.c_str()); return UMX_EINVAL; }
     fp.src = a.d; fp.S = a.h; fp.cin = a.c; fp.cout = sp.cout; fp.act = sp.act; fp.leaky = kLeaky;
+    fp.ks = sp.terms[0].k; fp.pool = sp.pool ? 1 : 0;
     float* d = nullptr;
     UMX_TRY(upload(h, sp.terms[0].w, &d)); fp.w = d;
     if (sp.has_bias) { UMX_TRY(upload(h, sp.bias, &d)); fp.bias = d; }
     const Buffer& ob = h->bufs[op.out_buf];
-    fp.out = ob.d; fp.out_h = ob.dh; fp.out_planes = ob.planes; fp.out_plane_elems = ob.plane_elems;
+    fp.out = ob.d; fp.out_h = ob.dh; fp.out_planes = ob.planes; fp.out_plane_elems = ob.plane_elems; fp.out_cs = ob.cs();
     return UMX_OK;
 }
 

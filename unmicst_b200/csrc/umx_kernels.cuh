@@ -57,12 +57,14 @@ struct FirstParams {
     const float* w;             // [9][cin][cout] fp32 (BN scale folded)
     const float* bias;          // [cout]
     int32_t n_tiles, S, cin, cout;
+    int32_t ks, pool;           // kernel size (3 or 5), fused 2x2 max-pool
     int32_t act;
     float leaky;
     float* out;                 // [n][S/2][S/2][cout] fp32 or nullptr
     __half* out_h;              // fp16 hi[/lo] planes or nullptr
     int64_t out_plane_elems;
     int32_t out_planes;
+    int32_t out_cs;             // channel stride of out_h (cout rounded up to 8)
 };
 
 struct TopParams {              // lt 1x1 conv (+ folded BN) + softmax over K classes
@@ -113,6 +115,7 @@ struct StitchParams {           // PI2D.patchOutput/getValidOutput as a gather +
 cudaError_t launch_conv_simt(const ConvParams& p, cudaStream_t s);
 cudaError_t launch_top_softmax(const TopParams& p, cudaStream_t s);
 cudaError_t launch_first_conv(const FirstParams& p, cudaStream_t s);
+size_t first_conv_smem_bytes(int cin, int ks, int cout);
 cudaError_t launch_gather_tiles(const GatherParams& p, cudaStream_t s);
 cudaError_t launch_stitch(const StitchParams& p, cudaStream_t s);
 cudaError_t conv_simt_configure();   // opt in to > 48 KB dynamic shared memory
