@@ -31,6 +31,14 @@ constexpr uint32_t kSpinLimit = 1u << 28;     // trap instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp; ptxas recognises the elect.sync idiom and keeps the single-thread region's
+// tcgen05 / TMA operands in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -256,7 +264,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int nch0 = (p.c0 + 63) >> 6, nch1 = (p.c1 + 63) >> 6;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ================= TMA producer =================
             if constexpr (HALO) {
                 const int hx0 = p.hx0, hy0 = p.hy0, n_chunks = nch0 + nch1, c0s = p.c0, n_t = p.n_t;
@@ -331,7 +339,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && leader) {
+        if (leader && elect_one()) {
             // ================= MMA issuer (leader CTA only in pair mode) =================
             const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_t >> 3) << 17) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
             int acc = 0; uint32_t acc_phase = 0;
