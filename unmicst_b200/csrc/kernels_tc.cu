@@ -24,7 +24,7 @@ namespace umx {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;               // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 constexpr int kAPlaneBytes = 128 * 128;       // 128 rows x 64 fp16
 constexpr int kAccStride = 256;               // TMEM columns between the two accumulator stages
 constexpr uint32_t kSpinLimit = 1u << 28;     // trap instead of hanging the GPU on a pipeline bug
@@ -215,6 +215,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     float* s_skipw = reinterpret_cast<float*>(tmem_slot + 4);
     float* s_topw = s_skipw + SKT * SKIPC * cpad;
     float* s_topb = s_topw + (p.top_w ? cpad * p.top_k : 0);
+    float* s_z = s_topb + 4;                     // [2 acc stages][128 pixels][4]: partial lt logits of the upper column half
     if (SKIPC > 0)
         for (int i = threadIdx.x; i < SKT * SKIPC * cpad; i += kThreads) {
             const int c = i % cpad;
@@ -237,7 +238,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if (lane == 0) {
             for (int s = 0; s < n_stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
             for (int s = 0; s < nb_stages; ++s) { mbar_init(fullB0 + 8 * s, 1); mbar_init(emptyB0 + 8 * s, 1); }
-            for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, PAIR ? 8 : 4); }
+            for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, PAIR ? 16 : 8); }
             fence_barrier_init();
         }
         __syncwarp();
@@ -442,7 +443,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
     } else {
         // ================= epilogue (4 warps, one TMEM lane quarter each) =================
-        const int q = warp & 3;
+        const int q = warp & 3;                                     // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;                           // which half of the N columns it handles
+        const int n16 = p.n_t >> 4;
+        const int c_lo = half == 0 ? 0 : (n16 + 1) >> 1;
+        const int c_hi = (p.exp_flags & 8) ? min(c_lo + 1, n16) : (half == 0 ? (n16 + 1) >> 1 : n16);
         const int m = q * 32 + lane;
         const int xl = m % p.bw, yl = (m / p.bw) % p.bh, nl = m / (p.bw * p.bh);
         int acc = 0; uint32_t acc_phase = 0;
@@ -472,7 +477,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
-            for (int c16 = 0; c16 < ((p.exp_flags & 8) ? 1 : (p.n_t >> 4)); ++c16) {
+            for (int c16 = c_lo; c16 < c_hi; ++c16) {
                 uint32_t r[16];
                 tmem_ld16(tbase + c16 * 16, r);
                 const int co = t.n_idx * p.n_t + c16 * 16;
@@ -552,7 +557,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 }
                 __syncwarp();        // reconverge before the next .sync.aligned TMEM load
             }
-            if (p.top_w && writer) {
+            if (p.top_w) {
+                // the two warps of a lane quarter hold the two column halves of each pixel: combine the partial logits
+                float* zs = s_z + ((size_t)acc * 128 + m) * 4;
+                if (half == 1) { zs[0] = z[0]; zs[1] = z[1]; zs[2] = z[2]; zs[3] = z[3]; }
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+                if (half == 0) { z[0] += zs[0]; z[1] += zs[1]; z[2] += zs[2]; z[3] += zs[3]; }
+            }
+            if (p.top_w && writer && half == 0) {
                 float mx = -INFINITY, sum = 0.f;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) if (k < p.top_k) { z[k] += s_topb[k]; mx = fmaxf(mx, z[k]); }
@@ -598,7 +610,7 @@ EncodeTiledFn encode_fn() {
 
 size_t tc_conv_fixed_bytes(const TcConvParams& p) {
     const size_t cpad = (size_t)p.n_ntiles * p.n_t;
-    const size_t tables = ((size_t)(p.skip_src ? p.skip_ntaps : 0) * p.skip_c * cpad + (p.top_w ? cpad * p.top_k + 4 : 0)) * sizeof(float);
+    const size_t tables = ((size_t)(p.skip_src ? p.skip_ntaps : 0) * p.skip_c * cpad + (p.top_w ? cpad * p.top_k + 4 + 2 * 128 * 4 : 0)) * sizeof(float);
     return (2 * (size_t)(p.stages + (p.halo ? p.b_stages : 0)) + 4) * 8 + 16 + tables + 1024;
 }
 size_t tc_conv_a_bytes(const TcConvParams& p) {
