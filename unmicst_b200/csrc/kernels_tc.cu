@@ -145,6 +145,14 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -216,6 +224,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     float* s_topw = s_skipw + SKT * SKIPC * cpad;
     float* s_topb = s_topw + (p.top_w ? cpad * p.top_k : 0);
     float* s_z = s_topb + 4;                     // [2 acc stages][128 pixels][4]: partial lt logits of the upper column half
+    float* s_bias = s_z + (p.top_w ? 2 * 128 * 4 : 0);       // [cpad] bias, then [cpad] post scale, [cpad] post shift
+    float* s_ps = s_bias + cpad;
+    float* s_pt = s_ps + (p.post_scale ? cpad : 0);
+    for (int i = threadIdx.x; i < cpad; i += kThreads) {
+        s_bias[i] = (p.bias && i < p.cout) ? p.bias[i] : 0.f;
+        if (p.post_scale) { s_ps[i] = i < p.cout ? p.post_scale[i] : 1.f; s_pt[i] = i < p.cout ? p.post_shift[i] : 0.f; }
+    }
     if (SKIPC > 0)
         for (int i = threadIdx.x; i < SKT * SKIPC * cpad; i += kThreads) {
             const int c = i % cpad;
@@ -477,16 +492,21 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
+            uint32_t rn[16];                                   // TMEM load of the next chunk is in flight while this one is processed
+            if (c_lo < c_hi) tmem_ld16_issue(tbase + c_lo * 16, rn);
             for (int c16 = c_lo; c16 < c_hi; ++c16) {
                 uint32_t r[16];
-                tmem_ld16(tbase + c16 * 16, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[j] = rn[j];
+                if (c16 + 1 < c_hi) tmem_ld16_issue(tbase + (c16 + 1) * 16, rn);
                 const int co = t.n_idx * p.n_t + c16 * 16;
                 float v[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float b = 0.f;
-                    if (p.bias && co + j < p.cout) b = __ldg(p.bias + co + j);
-                    v[j] = __uint_as_float(r[j]) + b;
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 b = *reinterpret_cast<const float4*>(s_bias + co + j4 * 4);
+                    v[j4 * 4 + 0] = __uint_as_float(r[j4 * 4 + 0]) + b.x; v[j4 * 4 + 1] = __uint_as_float(r[j4 * 4 + 1]) + b.y;
+                    v[j4 * 4 + 2] = __uint_as_float(r[j4 * 4 + 2]) + b.z; v[j4 * 4 + 3] = __uint_as_float(r[j4 * 4 + 3]) + b.w;
                 }
                 if (SKIPC > 0) {
 #pragma unroll
@@ -504,12 +524,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         }
                     }
                 }
+                if (p.act == ACT_LEAKY) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = act_fn(v[j], p.act, p.leaky);
+                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * p.leaky);       // leaky slope < 1
+                } else if (p.act == ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
                 if (p.post_scale) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (co + j < p.cout) v[j] = fmaf(v[j], __ldg(p.post_scale + co + j), __ldg(p.post_shift + co + j));
+                    for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], s_ps[co + j], s_pt[co + j]);
                 }
                 if (p.top_w) {
 #pragma unroll
@@ -542,17 +566,20 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         }
                     }
                     if (p.out_h && c < p.out_cs) {       // storage channels are padded to a multiple of 8; pad lanes hold 0
-                        __half2 hi[4], lo[4];
+                        __half2 hi[4];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float a = v[h8 * 8 + 2 * j], b = v[h8 * 8 + 2 * j + 1];
-                            const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
-                            hi[j] = __halves2half2(ha, hb);
-                            lo[j] = __halves2half2(__float2half_rn(a - __half2float(ha)), __float2half_rn(b - __half2float(hb)));
-                        }
+                        for (int j = 0; j < 4; ++j) hi[j] = __floats2half2_rn(v[h8 * 8 + 2 * j], v[h8 * 8 + 2 * j + 1]);
                         __half* o = p.out_h + opix * p.out_cs + c;
                         *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(hi);
-                        if (p.out_planes == 2) *reinterpret_cast<uint4*>(o + p.out_plane_elems) = *reinterpret_cast<uint4*>(lo);
+                        if (p.out_planes == 2) {
+                            __half2 lo[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 f = __half22float2(hi[j]);
+                                lo[j] = __floats2half2_rn(v[h8 * 8 + 2 * j] - f.x, v[h8 * 8 + 2 * j + 1] - f.y);
+                            }
+                            *reinterpret_cast<uint4*>(o + p.out_plane_elems) = *reinterpret_cast<uint4*>(lo);
+                        }
                     }
                 }
                 __syncwarp();        // reconverge before the next .sync.aligned TMEM load
@@ -610,7 +637,7 @@ EncodeTiledFn encode_fn() {
 
 size_t tc_conv_fixed_bytes(const TcConvParams& p) {
     const size_t cpad = (size_t)p.n_ntiles * p.n_t;
-    const size_t tables = ((size_t)(p.skip_src ? p.skip_ntaps : 0) * p.skip_c * cpad + (p.top_w ? cpad * p.top_k + 4 + 2 * 128 * 4 : 0)) * sizeof(float);
+    const size_t tables = ((size_t)(p.skip_src ? p.skip_ntaps : 0) * p.skip_c * cpad + (p.top_w ? cpad * p.top_k + 4 + 2 * 128 * 4 : 0) + cpad * (p.post_scale ? 3 : 1) + 8) * sizeof(float);
     return (2 * (size_t)(p.stages + (p.halo ? p.b_stages : 0)) + 4) * 8 + 16 + tables + 1024;
 }
 size_t tc_conv_a_bytes(const TcConvParams& p) {

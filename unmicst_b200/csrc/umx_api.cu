@@ -474,7 +474,8 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     const int skip_nt = mode == TC_SKIP_CONCAT ? ntaps_w : (mode == TC_SHORT_SKIP ? 1 : 0);
     {
         const size_t cpad = (size_t)tp.n_ntiles * tp.n_t;
-        const size_t tables = (size_t)skip_nt * skip_c * cpad * 4 + (op.fuse_top >= 0 ? (cpad * h->K + 8 + 2 * 128 * 4) * 4 : 0);
+        const size_t tables = (size_t)skip_nt * skip_c * cpad * 4 + (op.fuse_top >= 0 ? (cpad * h->K + 8 + 2 * 128 * 4) * 4 : 0)
+                              + cpad * (sp.has_post ? 3 : 1) * 4 + 64;
         const size_t budget = 227 * 1024 - 2048 - 512 - tables;
         const size_t bb = tc_conv_b_bytes(tp);
         if (tp.halo) {
