@@ -167,9 +167,12 @@ struct TileCoord { int phase, n0, y0, x0, n_idx; };
 // work item -> (phase, M unit, N tile); an M unit is one M tile, or a pair of M tiles in CTA-pair mode
 __device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int item, int m_units, int per_unit, int rank) {
     TileCoord t;
+    // N tile fastest, then the conv-transpose phase, then the M unit: the (<= 4) phases and the N tiles that read
+    // the same input pixels run back to back, so the input is fetched from HBM once and re-read from L2
     t.n_idx = item % p.n_ntiles;
-    const int mt = ((item / p.n_ntiles) % m_units) * per_unit + rank;
-    t.phase = item / (p.n_ntiles * m_units);
+    const int rest = item / p.n_ntiles;
+    t.phase = rest % p.nphase;
+    const int mt = (rest / p.nphase) * per_unit + rank;
     if (p.bn > 1) { t.n0 = mt * p.bn; t.y0 = 0; t.x0 = 0; }
     else {
         const int bx = p.in_w / p.bw, by = p.in_h / p.bh;
