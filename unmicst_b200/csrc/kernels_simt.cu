@@ -318,6 +318,35 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const FirstParams p) {
     }
 }
 
+// Tap expansion of the raw network input: out[n][y][x][tap*cin + c] = src[n][y+dy][x+dx][c] (0 outside the tile),
+// as fp16 hi[/lo] planes.  One thread per (pixel, group of 8 output channels): one 16-byte store per plane.
+__global__ void __launch_bounds__(256) taps_kernel(const TapsParams p) {
+    const int groups = p.cs >> 3;
+    const int64_t total = (int64_t)p.n_tiles * p.S * p.S * groups;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int g = (int)(i % groups);
+    const int64_t pix = i / groups;
+    const int x = (int)(pix % p.S), y = (int)((pix / p.S) % p.S);
+    const int64_t n = pix / ((int64_t)p.S * p.S);
+    const int r = p.ks / 2, nch = p.ks * p.ks * p.cin;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int ch = g * 8 + j;
+        float val = 0.f;
+        if (ch < nch) {
+            const int tap = ch / p.cin, c = ch - tap * p.cin;
+            const int yy = y + tap / p.ks - r, xx = x + tap % p.ks - r;
+            if (yy >= 0 && yy < p.S && xx >= 0 && xx < p.S) val = __ldg(p.src + ((n * p.S + yy) * p.S + xx) * p.cin + c);
+        }
+        v[j] = val;
+    }
+    __half* o = p.out + pix * p.cs + g * 8;
+    store_h2x4(o, p.out_plane_elems, p.out_planes, v);
+    store_h2x4(o + 4, p.out_plane_elems, p.out_planes, v + 4);
+}
+
 // One thread per pixel: K logits from cin channels, then a numerically stable softmax.
 template <int K>
 __global__ void __launch_bounds__(256) top_softmax_kernel(const TopParams p) {
@@ -516,6 +545,13 @@ cudaError_t launch_first_conv(const FirstParams& p, cudaStream_t s) {
     if (p.cin == 1 && p.ks == 5) return launch_first<1, 5>(p, grid, sm, s);
     if (p.cin == 2 && p.ks == 5) return launch_first<2, 5>(p, grid, sm, s);
     return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_taps(const TapsParams& p, cudaStream_t s) {
+    const int64_t total = (int64_t)p.n_tiles * p.S * p.S * (p.cs >> 3);
+    if (total == 0) return cudaSuccess;
+    taps_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_gather_tiles(const GatherParams& p, cudaStream_t s) {

@@ -63,15 +63,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (++spins > kSpinLimit) { printf("umx tc_conv: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
     }
 }
-// Polite wait for threads that are not on the critical path (epilogue, producer): back off between polls so the
-// MMA-issuing thread's barrier traffic is not contended.
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        __nanosleep(32);
-        if (++spins > (kSpinLimit >> 4)) { printf("umx tc_conv: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
-    }
-}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -116,32 +107,11 @@ __device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap
         "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
-__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
-// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row swizzle atoms 1024 B apart.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-__device__ __forceinline__ uint64_t umma_desc_sbo(uint32_t saddr, uint32_t sbo) {
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo >> 4) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -152,50 +122,215 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Cycle accounting for UMX_TC_DBG (exp_flags & 64): one thread per role adds its wait / work cycles to p.dbg[].
+struct DbgClock {
+    long long t; bool on;
+    __device__ __forceinline__ void start(bool enable) { on = enable; if (on) t = clock64(); }
+    __device__ __forceinline__ void lap(unsigned long long& acc) { if (on) { const long long n = clock64(); acc += (unsigned long long)(n - t); t = n; } }
+};
 
 struct TileCoord { int phase, n0, y0, x0, n_idx; };
 
-// work item -> (phase, M unit, N tile); an M unit is one M tile, or a pair of M tiles in CTA-pair mode
-__device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int item, int m_units, int per_unit, int rank) {
-    TileCoord t;
-    // N tile fastest, then the conv-transpose phase, then the M unit: the (<= 4) phases and the N tiles that read
-    // the same input pixels run back to back, so the input is fetched from HBM once and re-read from L2
-    t.n_idx = item % p.n_ntiles;
-    const int rest = item / p.n_ntiles;
-    t.phase = rest % p.nphase;
-    const int mt = (rest / p.nphase) * per_unit + rank;
-    if (p.bn > 1) { t.n0 = mt * p.bn; t.y0 = 0; t.x0 = 0; }
-    else {
-        const int bx = p.in_w / p.bw, by = p.in_h / p.bh;
-        t.n0 = mt / (bx * by);
-        const int r = mt % (bx * by);
-        t.y0 = (r / bx) * p.bh; t.x0 = (r % bx) * p.bw;
+// work item -> (phase, M unit, N tile); an M unit is one M tile, or a pair of M tiles in CTA-pair mode.
+// N tile fastest, then the conv-transpose phase, then the M unit: the (<= 4) phases and the N tiles that read the
+// same input pixels run back to back, so the input is fetched from HBM once and re-read from L2.
+// Division-free: grids and boxes are powers of two, nphase is 1 or 4, the N-tile count uses a magic multiplier.
+struct TileDecoder {
+    uint32_t nt_mul; int n_ntiles, ph_shift, per_unit, rank, bn, bx_shift, bxy_shift, bw, bh;
+    __device__ __forceinline__ void init(const TcConvParams& p, int per_unit_, int rank_) {
+        n_ntiles = p.n_ntiles; nt_mul = (uint32_t)((0x100000000ull + n_ntiles - 1) / (uint32_t)n_ntiles);
+        ph_shift = p.nphase == 4 ? 2 : 0; per_unit = per_unit_; rank = rank_; bn = p.bn; bw = p.bw; bh = p.bh;
+        bx_shift = 31 - __clz(p.in_w / p.bw); bxy_shift = bx_shift + 31 - __clz(p.in_h / p.bh);
     }
-    return t;
+    __device__ __forceinline__ TileCoord operator()(int item) const {
+        TileCoord t;
+        int rest = item; t.n_idx = 0;
+        if (n_ntiles > 1) { rest = (int)__umulhi((uint32_t)item, nt_mul); t.n_idx = item - rest * n_ntiles; }
+        t.phase = rest & ((1 << ph_shift) - 1);
+        const int mt = (rest >> ph_shift) * per_unit + rank;
+        if (bn > 1) { t.n0 = mt * bn; t.y0 = 0; t.x0 = 0; }
+        else {
+            t.n0 = mt >> bxy_shift;
+            const int r = mt & ((1 << bxy_shift) - 1);
+            t.y0 = (r >> bx_shift) * bh; t.x0 = (r & ((1 << bx_shift) - 1)) * bw;
+        }
+        return t;
+    }
+};
+
+// tcgen05.mma with the 64-bit shared-memory descriptors given as (lo, hi) register pairs: the hi words are loop
+// invariant and the lo words advance by plain 32-bit adds, so one MMA costs two adds and the instruction itself.
+template <bool PAIR>
+__device__ __forceinline__ void umma_issue(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc, uint32_t accumulate) {
+    if (PAIR)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+            ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+            ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+// lo / hi words of the shared-memory descriptor of a K-major, 128B-swizzled operand tile (rows of 128 B, 8-row swizzle
+// atoms `sbo` bytes apart): lo = start address >> 4 | LBO (unused, 1) << 16; hi = SBO >> 4 | version 1 << 14 | SWIZZLE_128B << 29
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo) { return (sbo >> 4) | (1u << 14) | (2u << 29); }
+
+// tcgen05.mma that always accumulates (every MMA of a work item but the first)
+template <bool PAIR>
+__device__ __forceinline__ void umma_acc(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+    if (PAIR)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.eq.b32 p, 0, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+            ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc) : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.eq.b32 p, 0, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+            ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc) : "memory");
 }
 
-__device__ __forceinline__ float act_fn(float v, int act, float leaky) {
-    if (act == ACT_RELU) return fmaxf(v, 0.f);
-    if (act == ACT_LEAKY) return v > 0.f ? v : v * leaky;
-    return v;
+// The nk <= 4 MMAs (one per 16 channels) of a 64-channel slab; in split mode each product is hi*hi + hi*lo + lo*hi.
+// Only the very first MMA of a work item carries a run-time accumulate flag.
+template <bool PAIR>
+__device__ __forceinline__ void umma_slab(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                          int nk, bool split, uint32_t a_plane16, uint32_t b_plane16, uint32_t& accumulate, int exp = 0) {
+    if (exp & 128) return;                       // timing experiment: the issue loop without the MMAs
+    umma_issue<PAIR>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+    accumulate = 1;
+    if (!split) {
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+            if (k < nk) umma_acc<PAIR>(tmem_d, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc);
+    } else {
+        umma_acc<PAIR>(tmem_d, a_lo, a_hi, b_lo + b_plane16, b_hi, idesc);
+        umma_acc<PAIR>(tmem_d, a_lo + a_plane16, a_hi, b_lo, b_hi, idesc);
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+            if (k < nk) {
+                umma_acc<PAIR>(tmem_d, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc);
+                umma_acc<PAIR>(tmem_d, a_lo + 2 * k, a_hi, b_lo + b_plane16 + 2 * k, b_hi, idesc);
+                umma_acc<PAIR>(tmem_d, a_lo + a_plane16 + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc);
+            }
+    }
 }
 
-// SKIPC = channels of the narrow fp32 source folded into the epilogue (0 = none), SKT = its tap count.
-template <int SKIPC, int SKT, bool PAIR, bool HALO>
+// Everything the epilogue of one accumulator tile needs that does not change from item to item.
+struct EpiCtx {
+    const float* s_bias; const float* s_ps; const float* s_pt; const float* s_skipw; const float4* s_topw4;
+    float* out_f; __half* out_h; int64_t out_plane_elems;
+    int cout, out_cs, out_planes, act, pool, bw;
+    float leaky;
+    bool has_post;
+};
+
+// Bias / shortcut / activation / post-affine of NC accumulator columns of one pixel, then either the fused lt logits
+// (TOPK > 0) or the 2x2 max-pool and the fp32 / fp16 hi[/lo] stores.  co = absolute output channel of column 0.
+template <int NC, int SKIPC, int TOPK>
+__device__ __forceinline__ void epi_chunk(const EpiCtx& e, const uint32_t (&r)[NC], int co, float xs, bool writer,
+                                          float* of, __half* oh, float (&z)[4]) {
+    float v[NC];
+#pragma unroll
+    for (int j4 = 0; j4 < NC / 4; ++j4) {
+        const float4 b = *reinterpret_cast<const float4*>(e.s_bias + co + j4 * 4);
+        v[j4 * 4 + 0] = __uint_as_float(r[j4 * 4 + 0]) + b.x; v[j4 * 4 + 1] = __uint_as_float(r[j4 * 4 + 1]) + b.y;
+        v[j4 * 4 + 2] = __uint_as_float(r[j4 * 4 + 2]) + b.z; v[j4 * 4 + 3] = __uint_as_float(r[j4 * 4 + 3]) + b.w;
+    }
+    if (SKIPC > 0) {            // 1x1 shortcut of a one-channel source (legacy down layers, UnMicst.py:95-97)
+#pragma unroll
+        for (int j4 = 0; j4 < NC / 4; ++j4) {
+            const float4 w = *reinterpret_cast<const float4*>(e.s_skipw + co + j4 * 4);
+            v[j4 * 4 + 0] = fmaf(xs, w.x, v[j4 * 4 + 0]); v[j4 * 4 + 1] = fmaf(xs, w.y, v[j4 * 4 + 1]);
+            v[j4 * 4 + 2] = fmaf(xs, w.z, v[j4 * 4 + 2]); v[j4 * 4 + 3] = fmaf(xs, w.w, v[j4 * 4 + 3]);
+        }
+    }
+    if (e.act == ACT_LEAKY) {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) v[j] = fmaxf(v[j], v[j] * e.leaky);       // leaky slope < 1
+    } else if (e.act == ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (e.has_post) {
+#pragma unroll
+        for (int j4 = 0; j4 < NC / 4; ++j4) {
+            const float4 a = *reinterpret_cast<const float4*>(e.s_ps + co + j4 * 4);
+            const float4 b = *reinterpret_cast<const float4*>(e.s_pt + co + j4 * 4);
+            v[j4 * 4 + 0] = fmaf(v[j4 * 4 + 0], a.x, b.x); v[j4 * 4 + 1] = fmaf(v[j4 * 4 + 1], a.y, b.y);
+            v[j4 * 4 + 2] = fmaf(v[j4 * 4 + 2], a.z, b.z); v[j4 * 4 + 3] = fmaf(v[j4 * 4 + 3], a.w, b.w);
+        }
+    }
+    if (TOPK > 0) {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            const float4 w = e.s_topw4[co + j];
+            z[0] = fmaf(v[j], w.x, z[0]); z[1] = fmaf(v[j], w.y, z[1]);
+            if (TOPK > 2) z[2] = fmaf(v[j], w.z, z[2]);
+            if (TOPK > 3) z[3] = fmaf(v[j], w.w, z[3]);
+        }
+        return;
+    }
+    if (e.pool) {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], e.bw));
+        }
+    }
+    if (!writer) return;
+#pragma unroll
+    for (int h8 = 0; h8 < NC / 8; ++h8) {
+        const int c = co + h8 * 8;
+        if (e.out_f != nullptr && c < e.cout) {
+            float* o = of + h8 * 8;
+            if (c + 8 <= e.cout && !(e.cout & 3)) {
+                reinterpret_cast<float4*>(o)[0] = make_float4(v[h8 * 8 + 0], v[h8 * 8 + 1], v[h8 * 8 + 2], v[h8 * 8 + 3]);
+                reinterpret_cast<float4*>(o)[1] = make_float4(v[h8 * 8 + 4], v[h8 * 8 + 5], v[h8 * 8 + 6], v[h8 * 8 + 7]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (c + j < e.cout) o[j] = v[h8 * 8 + j];
+            }
+        }
+        if (e.out_h != nullptr && c < e.out_cs) {       // storage channels are padded to a multiple of 8; pad lanes hold 0
+            __half2 hi[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hi[j] = __floats2half2_rn(v[h8 * 8 + 2 * j], v[h8 * 8 + 2 * j + 1]);
+            __half* o = oh + h8 * 8;
+            *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(hi);
+            if (e.out_planes == 2) {
+                __half2 lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(hi[j]);
+                    lo[j] = __floats2half2_rn(v[h8 * 8 + 2 * j] - f.x, v[h8 * 8 + 2 * j + 1] - f.y);
+                }
+                *reinterpret_cast<uint4*>(o + e.out_plane_elems) = *reinterpret_cast<uint4*>(lo);
+            }
+        }
+    }
+}
+
+// SKIPC = 1: a one-channel fp32 source enters as a 1x1 shortcut in the epilogue.  TOPK = classes of the fused
+// lt 1x1 conv + softmax (0: the activation is stored instead).
+template <int SKIPC, int TOPK, bool PAIR, bool HALO>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ TcConvParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment for the 128B swizzle; computed as an offset so the pointers stay provably shared-space
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     // Plain mode: one ring of `stages` slots, each [A tile planes][B tile planes] for one (tap, 64-channel slab).
     // Halo mode (high-resolution layers): ring A holds one (bh+halo) x (bw+halo) pixel patch per slab that serves
     // every tap (A is fetched from L2 once instead of once per tap); ring B holds the weights of `gb` taps per slot.
@@ -220,28 +355,26 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const uint32_t tfull0 = emptyB0 + 8 * nb_stages;
     const uint32_t tempty0 = tfull0 + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * n_stages + 2 * nb_stages + 4);
-    // small fp32 tables for the epilogue: skip-term weights [9][SKIPC][cout], lt weights [cout][K], lt bias [K]
-    // (rows padded with zeros to cpad = n_ntiles * n_t columns so the epilogue needs no channel guards)
+    // small fp32 tables for the epilogue (rows padded with zeros to cpad = n_ntiles * n_t columns so the epilogue
+    // needs no channel guards): bias [cpad], post scale / shift [cpad] each, shortcut weights [cpad],
+    // lt weights [cpad] x float4, lt bias [4], partial lt logits [2 acc stages][128 pixels][4]
     const int cpad = p.n_ntiles * p.n_t;
-    float* s_skipw = reinterpret_cast<float*>(tmem_slot + 4);
-    float* s_topw = s_skipw + SKT * SKIPC * cpad;
-    float* s_topb = s_topw + (p.top_w ? cpad * p.top_k : 0);
-    float* s_z = s_topb + 4;                     // [2 acc stages][128 pixels][4]: partial lt logits of the upper column half
-    float* s_bias = s_z + (p.top_w ? 2 * 128 * 4 : 0);       // [cpad] bias, then [cpad] post scale, [cpad] post shift
+    float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
     float* s_ps = s_bias + cpad;
     float* s_pt = s_ps + (p.post_scale ? cpad : 0);
+    float* s_skipw = s_pt + (p.post_scale ? cpad : 0);
+    float* s_topw = s_skipw + (SKIPC > 0 ? cpad : 0);
+    float* s_topb = s_topw + (TOPK > 0 ? 4 * cpad : 0);
+    float* s_z = s_topb + 4;
     for (int i = threadIdx.x; i < cpad; i += kThreads) {
         s_bias[i] = (p.bias && i < p.cout) ? p.bias[i] : 0.f;
         if (p.post_scale) { s_ps[i] = i < p.cout ? p.post_scale[i] : 1.f; s_pt[i] = i < p.cout ? p.post_shift[i] : 0.f; }
+        if (SKIPC > 0) s_skipw[i] = i < p.cout ? p.skip_w[i] : 0.f;
     }
-    if (SKIPC > 0)
-        for (int i = threadIdx.x; i < SKT * SKIPC * cpad; i += kThreads) {
-            const int c = i % cpad;
-            s_skipw[i] = c < p.cout ? p.skip_w[(i / cpad) * p.cout + c] : 0.f;
-        }
-    if (p.top_w) {
-        for (int i = threadIdx.x; i < cpad * p.top_k; i += kThreads) s_topw[i] = (i / p.top_k) < p.cout ? p.top_w[i] : 0.f;
-        if (threadIdx.x < p.top_k) s_topb[threadIdx.x] = p.top_b ? p.top_b[threadIdx.x] : 0.f;
+    if (TOPK > 0) {
+        for (int i = threadIdx.x; i < cpad * 4; i += kThreads)
+            s_topw[i] = ((i >> 2) < p.cout && (i & 3) < TOPK) ? p.top_w[(i >> 2) * TOPK + (i & 3)] : 0.f;
+        if (threadIdx.x < 4) s_topb[threadIdx.x] = (p.top_b && (int)threadIdx.x < TOPK) ? p.top_b[threadIdx.x] : 0.f;
     }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -281,127 +414,159 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int item_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int nch0 = (p.c0 + 63) >> 6, nch1 = (p.c1 + 63) >> 6;
+    TileDecoder decode; decode.init(p, per_unit, rank);
+    const bool dbg_on = (p.exp_flags & 64) && p.dbg != nullptr;
 
     if (warp == 0) {
         if (elect_one()) {
             // ================= TMA producer =================
+            const int n_t = p.n_t, c0s = p.c0;
+            const bool a1c = p.a1_center != 0; const int ctap = p.center_tap;
+            const bool noload = (p.exp_flags & 1) != 0;          // timing experiment: barriers complete without any TMA traffic
             if constexpr (HALO) {
-                const int hx0 = p.hx0, hy0 = p.hy0, n_chunks = nch0 + nch1, c0s = p.c0, n_t = p.n_t;
-                const bool a1c = p.a1_center != 0; const int ctap = p.center_tap;
+                const int hx0 = p.hx0, hy0 = p.hy0, n_chunks = nch0 + nch1;
                 const uint32_t txA = (PAIR ? 2u : 1u) * (uint32_t)(planes * a_box_bytes);
                 int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+                unsigned long long c_wa = 0, c_wb = 0, c_work = 0; DbgClock clk; clk.start(dbg_on);
                 for (int tile = item0; tile < total; tile += item_step) {
-                    const TileCoord t = decode_tile(p, tile, m_units, per_unit, rank);
-                    const int ntap = p.ntaps[t.phase];
+                    const TileCoord t = decode(tile);
+                    const TcPhaseGrid g = p.grid[t.phase];
                     const int ncol = t.n_idx * n_t + (PAIR ? rank * (n_t / 2) : 0);
+                    const int ax = t.x0 - hx0, ay = t.y0 - hy0;
                     for (int cb = 0; cb < n_chunks; ++cb) {
                         const bool second = cb >= nch0;
                         const int cc = (second ? cb - nch0 : cb) * 64;
                         const CUtensorMap* mapA = second ? &mapA1 : &mapA0;
+                        clk.lap(c_work);
                         mbar_wait(empty0 + 8 * sa, pa ^ 1);
+                        clk.lap(c_wa);
                         const uint32_t fa = full0 + 8 * sa;
-                        const uint32_t da = smem_u32(smem + (size_t)sa * stage_bytes);
-                        if (leader) mbar_expect_tx(fa, txA);
-                        for (int pl = 0; pl < planes; ++pl) {
-                            if (PAIR) tma_load_5d_pair(da + pl * a_plane_bytes, mapA, fa, cc, t.x0 - hx0, t.y0 - hy0, t.n0, pl);
-                            else tma_load_5d(da + pl * a_plane_bytes, mapA, fa, cc, t.x0 - hx0, t.y0 - hy0, t.n0, pl);
+                        const uint32_t da = smem_u32(smem) + (uint32_t)(sa * stage_bytes);
+                        if (noload) { if (leader) mbar_arrive(fa); }
+                        else if (leader) mbar_expect_tx(fa, txA);
+                        for (int pl = 0; pl < planes && !noload; ++pl) {
+                            if (PAIR) tma_load_5d_pair(da + pl * a_plane_bytes, mapA, fa, cc, ax, ay, t.n0, pl);
+                            else tma_load_5d(da + pl * a_plane_bytes, mapA, fa, cc, ax, ay, t.n0, pl);
                         }
                         if (++sa == n_stages) { sa = 0; pa ^= 1; }
-                        const int tb = (second && a1c) ? ctap : 0, te = (second && a1c) ? ctap + 1 : ntap;
-                        for (int t0 = tb; t0 < te; t0 += gb) {
+                        const bool centre_only = second && a1c;        // 1x1 term: its slabs exist at the centre tap only
+                        const int te = centre_only ? 1 : g.ntaps;
+                        const int kc = (second ? c0s : 0) + cc;
+                        int wi = centre_only ? ctap : g.wi0, ix = 0;
+                        for (int t0 = 0; t0 < te; t0 += gb) {
                             const int ng = min(gb, te - t0);
+                            clk.lap(c_work);
                             mbar_wait(emptyB0 + 8 * sb, pb ^ 1);
+                            clk.lap(c_wb);
                             const uint32_t fb = fullB0 + 8 * sb;
-                            const uint32_t db = smem_u32(smem_b + (size_t)sb * gb * b_bytes);
-                            if (leader) mbar_expect_tx(fb, (PAIR ? 2u : 1u) * (uint32_t)(ng * b_bytes));
-                            for (int j = 0; j < ng; ++j) {
-                                const int wi = p.taps[t.phase][t0 + j].wi;
-                                if (PAIR) tma_load_4d_pair(db + j * b_bytes, &mapB, fb, (second ? c0s : 0) + cc, ncol, wi, 0);
-                                else tma_load_4d(db + j * b_bytes, &mapB, fb, (second ? c0s : 0) + cc, ncol, wi, 0);
+                            uint32_t db = smem_u32(smem_b) + (uint32_t)(sb * gb * b_bytes);
+                            if (noload) { if (leader) mbar_arrive(fb); }
+                            else if (leader) mbar_expect_tx(fb, (PAIR ? 2u : 1u) * (uint32_t)(ng * b_bytes));
+                            for (int j = 0; j < ng && !noload; ++j, db += b_bytes) {
+                                if (PAIR) tma_load_4d_pair(db, &mapB, fb, kc, ncol, wi, 0);
+                                else tma_load_4d(db, &mapB, fb, kc, ncol, wi, 0);
+                                wi += g.wix;
+                                if (++ix == g.nx) { ix = 0; wi += g.wiy - g.nx * g.wix; }
                             }
                             if (++sb == nb_stages) { sb = 0; pb ^= 1; }
                         }
                     }
                 }
+                clk.lap(c_work);
+                if (dbg_on && leader) { atomicAdd(p.dbg + 0, c_wa); atomicAdd(p.dbg + 1, c_wb); atomicAdd(p.dbg + 2, c_work); }
             } else {
-            int stage = 0; uint32_t phase = 0;
-            for (int tile = item0; tile < total; tile += item_step) {
-                const TileCoord t = decode_tile(p, tile, m_units, per_unit, rank);
-                const int ntap = p.ntaps[t.phase];
-                for (int tp = 0; tp < ntap; ++tp) {
-                    const TcTap tap = p.taps[t.phase][tp];
-                    const int nchunks_tp = nch0 + ((p.a1_center && tp != p.center_tap) ? 0 : nch1);
-                    for (int c0 = 0; c0 < nchunks_tp; c0 += ks) {
-                        const int ns = min(ks, nchunks_tp - c0);
-                        mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                        const uint32_t fb = full0 + 8 * stage;
-                        const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
-                        if (leader) mbar_expect_tx(fb, (PAIR ? 2u : 1u) * (uint32_t)(ns * slab_bytes));
-                        for (int j = 0; j < ns; ++j) {
-                            const int cb = c0 + j;
-                            const bool second = cb >= nch0;
-                            const int cc = (second ? cb - nch0 : cb) * 64;
-                            const uint32_t sa = sbase + j * slab_bytes;
-                            if (PAIR) {
-                                tma_load_5d_pair(sa, second ? &mapA1 : &mapA0, fb, cc, t.x0 + tap.dx, t.y0 + tap.dy, t.n0, 0);
-                                tma_load_4d_pair(sa + a_bytes, &mapB, fb, (second ? p.c0 : 0) + cc,
-                                                 t.n_idx * p.n_t + rank * (p.n_t / 2), tap.wi, 0);
-                            } else {
-                                tma_load_5d(sa, second ? &mapA1 : &mapA0, fb, cc, t.x0 + tap.dx, t.y0 + tap.dy, t.n0, 0);
-                                tma_load_4d(sa + a_bytes, &mapB, fb, (second ? p.c0 : 0) + cc, t.n_idx * p.n_t, tap.wi, 0);
+                int stage = 0; uint32_t phase = 0;
+                unsigned long long c_wa = 0, c_work = 0; DbgClock clk; clk.start(dbg_on);
+                for (int tile = item0; tile < total; tile += item_step) {
+                    const TileCoord t = decode(tile);
+                    const TcPhaseGrid g = p.grid[t.phase];
+                    const int ncol = t.n_idx * n_t + (PAIR ? rank * (n_t / 2) : 0);
+                    int wi = g.wi0, ix = 0, ax = t.x0 + g.dx0, ay = t.y0 + g.dy0;
+                    for (int tp = 0; tp < g.ntaps; ++tp) {
+                        const int nchunks_tp = nch0 + ((a1c && tp != ctap) ? 0 : nch1);
+                        for (int c0 = 0; c0 < nchunks_tp; c0 += ks) {
+                            const int ns = min(ks, nchunks_tp - c0);
+                            clk.lap(c_work);
+                            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                            clk.lap(c_wa);
+                            const uint32_t fb = full0 + 8 * stage;
+                            uint32_t sa = smem_u32(smem) + (uint32_t)(stage * stage_bytes);
+                            if (noload) { if (leader) mbar_arrive(fb); }
+                            else if (leader) mbar_expect_tx(fb, (PAIR ? 2u : 1u) * (uint32_t)(ns * slab_bytes));
+                            for (int j = 0; j < ns && !noload; ++j, sa += slab_bytes) {
+                                const int cb = c0 + j;
+                                const bool second = cb >= nch0;
+                                const int cc = (second ? cb - nch0 : cb) * 64;
+                                if (PAIR) {
+                                    tma_load_5d_pair(sa, second ? &mapA1 : &mapA0, fb, cc, ax, ay, t.n0, 0);
+                                    tma_load_4d_pair(sa + a_bytes, &mapB, fb, (second ? c0s : 0) + cc, ncol, wi, 0);
+                                } else {
+                                    tma_load_5d(sa, second ? &mapA1 : &mapA0, fb, cc, ax, ay, t.n0, 0);
+                                    tma_load_4d(sa + a_bytes, &mapB, fb, (second ? c0s : 0) + cc, ncol, wi, 0);
+                                }
                             }
+                            if (++stage == n_stages) { stage = 0; phase ^= 1; }
                         }
-                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        wi += g.wix; ax += g.dstep;
+                        if (++ix == g.nx) { ix = 0; wi += g.wiy - g.nx * g.wix; ax = t.x0 + g.dx0; ay += g.dstep; }
                     }
                 }
-            }
+                clk.lap(c_work);
+                if (dbg_on && leader) { atomicAdd(p.dbg + 0, c_wa); atomicAdd(p.dbg + 2, c_work); }
             }
         }
     } else if (warp == 1) {
         if (leader && elect_one()) {
             // ================= MMA issuer (leader CTA only in pair mode) =================
             const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_t >> 3) << 17) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
+            const bool split = planes == 2;
+            const uint32_t a_plane16 = (uint32_t)a_plane_bytes >> 4, b_plane16 = (uint32_t)b_plane_bytes >> 4;
+            const uint32_t b_hi = desc_hi(1024);
+            const bool a1c = p.a1_center != 0; const int ctap = p.center_tap;
+            const int nk_last0 = (((p.c0 - 1) & 63) + 16) >> 4, nk_last1 = nch1 ? (((p.c1 - 1) & 63) + 16) >> 4 : 0;   // MMAs of the last slab
+            const bool one_mma = (p.exp_flags & 4) != 0;
+            const int exp_mma = p.exp_flags & (128 | 256);
             int acc = 0; uint32_t acc_phase = 0;
+            unsigned long long c_wt = 0, c_wa = 0, c_wb = 0, c_work = 0; DbgClock clk; clk.start(dbg_on);
             if constexpr (HALO) {
-                const int pw = p.pw, hx0 = p.hx0, hy0 = p.hy0, n_chunks = nch0 + nch1, c0s = p.c0, c1s = p.c1;
-                const bool a1c = p.a1_center != 0; const int ctap = p.center_tap;
-                const uint32_t a_sbo = (uint32_t)pw * 128u;         // consecutive 8-pixel rows are one patch row apart
+                const int pw = p.pw, hx0 = p.hx0, hy0 = p.hy0, n_chunks = nch0 + nch1;
+                const uint32_t a_hi = desc_hi((uint32_t)pw * 128u);     // consecutive 8-pixel rows are one patch row apart
+                const uint32_t b16 = (uint32_t)b_bytes >> 4;
                 int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
                 for (int tile = item0; tile < total; tile += item_step) {
-                    const TileCoord t = decode_tile(p, tile, m_units, per_unit, rank);
-                    const int ntap = p.ntaps[t.phase];
+                    const TcPhaseGrid g = p.grid[decode(tile).phase];
+                    // A offset (in 16-byte units) of tap (iy, ix) inside the patch: off0 + iy*sy + ix*sx
+                    const int sx = g.dstep * 8, sy = g.dstep * pw * 8, row_back = sy - g.nx * sx;
+                    const uint32_t off0 = (uint32_t)(((g.dy0 + hy0) * pw + g.dx0 + hx0) * 8);
+                    clk.lap(c_work);
                     mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+                    clk.lap(c_wt);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccStride);
                     uint32_t accumulate = 0;
                     for (int cb = 0; cb < n_chunks; ++cb) {
                         const bool second = cb >= nch0;
-                        const int kvalid = min(64, (second ? c1s : c0s) - (second ? cb - nch0 : cb) * 64);
-                        const int nk = (kvalid + 15) >> 4;
+                        const int nk = one_mma ? 1 : (cb == nch0 - 1 ? nk_last0 : (cb == n_chunks - 1 ? nk_last1 : 4));
+                        clk.lap(c_work);
                         mbar_wait(full0 + 8 * sa, pa);
+                        clk.lap(c_wa);
                         tc_fence_after();
-                        const uint32_t abase = smem_u32(smem + (size_t)sa * stage_bytes);
-                        const int tb = (second && a1c) ? ctap : 0, te = (second && a1c) ? ctap + 1 : ntap;
-                        for (int t0 = tb; t0 < te; t0 += gb) {
+                        const uint32_t a_lo0 = desc_lo(smem_u32(smem) + (uint32_t)(sa * stage_bytes));
+                        const bool centre_only = second && a1c;
+                        const int te = centre_only ? 1 : g.ntaps;
+                        uint32_t a_lo = a_lo0 + (centre_only ? (uint32_t)((hy0 * pw + hx0) * 8) : off0);
+                        int ix = 0;
+                        for (int t0 = 0; t0 < te; t0 += gb) {
                             const int ng = min(gb, te - t0);
+                            clk.lap(c_work);
                             mbar_wait(fullB0 + 8 * sb, pb);
+                            clk.lap(c_wb);
                             tc_fence_after();
-                            const uint32_t bbase = smem_u32(smem_b + (size_t)sb * gb * b_bytes);
-                            for (int j = 0; j < ng; ++j) {
-                                const TcTap tap = p.taps[t.phase][t0 + j];
-                                const uint32_t sa_t = abase + (uint32_t)((tap.dy + hy0) * pw + tap.dx + hx0) * 128u;
-                                const uint32_t sb_t = bbase + j * b_bytes;
-                                for (int k = 0; k < nk; ++k) {
-                                    const uint64_t ah = umma_desc_sbo(sa_t + k * 32, a_sbo), bh = umma_desc(sb_t + k * 32);
-                                    if (PAIR) umma_f16_pair(tmem_d, ah, bh, idesc, accumulate); else umma_f16(tmem_d, ah, bh, idesc, accumulate);
-                                    accumulate = 1;
-                                    if (planes == 2) {
-                                        const uint64_t al = umma_desc_sbo(sa_t + a_plane_bytes + k * 32, a_sbo);
-                                        const uint64_t bl = umma_desc(sb_t + b_plane_bytes + k * 32);
-                                        if (PAIR) { umma_f16_pair(tmem_d, ah, bl, idesc, 1); umma_f16_pair(tmem_d, al, bh, idesc, 1); }
-                                        else { umma_f16(tmem_d, ah, bl, idesc, 1); umma_f16(tmem_d, al, bh, idesc, 1); }
-                                    }
-                                }
+                            uint32_t b_lo = desc_lo(smem_u32(smem_b) + (uint32_t)(sb * gb * b_bytes));
+                            for (int j = 0; j < ng; ++j, b_lo += b16) {
+                                umma_slab<PAIR>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, nk, split, a_plane16, b_plane16, accumulate, exp_mma);
+                                a_lo += sx;
+                                if (++ix == g.nx) { ix = 0; a_lo += row_back; }
                             }
                             if (PAIR) umma_commit_pair(emptyB0 + 8 * sb); else umma_commit(emptyB0 + 8 * sb);
                             if (++sb == nb_stages) { sb = 0; pb ^= 1; }
@@ -413,202 +578,132 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
             } else {
-            int stage = 0; uint32_t phase = 0;
-            for (int tile = item0; tile < total; tile += item_step) {
-                const TileCoord t = decode_tile(p, tile, m_units, per_unit, rank);
-                const int ntap = p.ntaps[t.phase];
-                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccStride);
-                uint32_t accumulate = 0;
-                for (int tp = 0; tp < ntap; ++tp) {
-                    const int nchunks_tp = nch0 + ((p.a1_center && tp != p.center_tap) ? 0 : nch1);
-                    for (int c0 = 0; c0 < nchunks_tp; c0 += ks) {
-                        const int ns = min(ks, nchunks_tp - c0);
-                        mbar_wait(full0 + 8 * stage, phase);
-                        tc_fence_after();
-                        const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
-                        for (int j = 0; j < ns; ++j) {
-                        const int cb = c0 + j;
-                        const bool second = cb >= nch0;
-                        const int cc = (second ? cb - nch0 : cb) * 64;
-                        const int kvalid = min(64, (second ? p.c1 : p.c0) - cc);
-                        const int nk = (p.exp_flags & 4) ? 1 : (kvalid + 15) >> 4;
-                        const uint32_t sa = sbase + j * slab_bytes;
-                        const uint32_t sb = sa + a_bytes;
-                        for (int k = 0; k < nk; ++k) {
-                            const uint64_t ah = umma_desc(sa + k * 32), bh = umma_desc(sb + k * 32);
-                            if (PAIR) umma_f16_pair(tmem_d, ah, bh, idesc, accumulate); else umma_f16(tmem_d, ah, bh, idesc, accumulate);
-                            accumulate = 1;
-                            if (p.planes == 2) {
-                                const uint64_t al = umma_desc(sa + kAPlaneBytes + k * 32);
-                                const uint64_t bl = umma_desc(sb + b_plane_bytes + k * 32);
-                                if (PAIR) { umma_f16_pair(tmem_d, ah, bl, idesc, 1); umma_f16_pair(tmem_d, al, bh, idesc, 1); }
-                                else { umma_f16(tmem_d, ah, bl, idesc, 1); umma_f16(tmem_d, al, bh, idesc, 1); }
+                const uint32_t a_hi = b_hi;
+                const uint32_t slab16 = (uint32_t)slab_bytes >> 4, ab16 = (uint32_t)a_bytes >> 4;
+                int stage = 0; uint32_t phase = 0;
+                for (int tile = item0; tile < total; tile += item_step) {
+                    const int ntap = p.grid[decode(tile).phase].ntaps;
+                    clk.lap(c_work);
+                    mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+                    clk.lap(c_wt);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccStride);
+                    uint32_t accumulate = 0;
+                    for (int tp = 0; tp < ntap; ++tp) {
+                        const int nchunks_tp = nch0 + ((a1c && tp != ctap) ? 0 : nch1);
+                        for (int c0 = 0; c0 < nchunks_tp; c0 += ks) {
+                            const int ns = min(ks, nchunks_tp - c0);
+                            clk.lap(c_work);
+                            mbar_wait(full0 + 8 * stage, phase);
+                            clk.lap(c_wa);
+                            tc_fence_after();
+                            uint32_t a_lo = desc_lo(smem_u32(smem) + (uint32_t)(stage * stage_bytes));
+                            for (int j = 0; j < ns; ++j, a_lo += slab16) {
+                                const int cb = c0 + j;
+                                const int nk = one_mma ? 1 : (cb == nch0 - 1 ? nk_last0 : (cb == nch0 + nch1 - 1 ? nk_last1 : 4));
+                                umma_slab<PAIR>(tmem_d, a_lo, a_hi, a_lo + ab16, b_hi, idesc, nk, split, a_plane16, b_plane16, accumulate, exp_mma);
                             }
+                            // frees the smem slot (in both CTAs) when these MMAs retire
+                            if (PAIR) umma_commit_pair(empty0 + 8 * stage); else umma_commit(empty0 + 8 * stage);
+                            if (++stage == n_stages) { stage = 0; phase ^= 1; }
                         }
-                        }
-                        // frees the smem slot (in both CTAs) when these MMAs retire
-                        if (PAIR) umma_commit_pair(empty0 + 8 * stage); else umma_commit(empty0 + 8 * stage);
-                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
+                    // accumulator ready for the epilogue (of both CTAs)
+                    if (PAIR) umma_commit_pair(tfull0 + 8 * acc); else umma_commit(tfull0 + 8 * acc);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
-                // accumulator ready for the epilogue (of both CTAs)
-                if (PAIR) umma_commit_pair(tfull0 + 8 * acc); else umma_commit(tfull0 + 8 * acc);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            }
+            clk.lap(c_work);
+            if (dbg_on) { atomicAdd(p.dbg + 4, c_wt); atomicAdd(p.dbg + 5, c_wa); atomicAdd(p.dbg + 6, c_wb); atomicAdd(p.dbg + 7, c_work); atomicAdd(p.dbg + 15, 1ull); }
         }
     } else {
-        // ================= epilogue (4 warps, one TMEM lane quarter each) =================
+        // ================= epilogue (8 warps: two per TMEM lane quarter, each half of the N columns) =================
         const int q = warp & 3;                                     // TMEM lane quarter this warp may read
         const int half = (warp - 2) >> 2;                           // which half of the N columns it handles
-        const int n16 = p.n_t >> 4;
-        const int c_lo = half == 0 ? 0 : (n16 + 1) >> 1;
-        const int c_hi = (p.exp_flags & 8) ? min(c_lo + 1, n16) : (half == 0 ? (n16 + 1) >> 1 : n16);
+        EpiCtx e;
+        e.s_bias = s_bias; e.s_ps = s_ps; e.s_pt = s_pt; e.s_skipw = s_skipw; e.s_topw4 = reinterpret_cast<const float4*>(s_topw);
+        e.out_f = p.out_f; e.out_h = p.out_h; e.out_plane_elems = p.out_plane_elems;
+        e.cout = p.cout; e.out_cs = p.out_cs; e.out_planes = p.out_planes; e.act = p.act; e.pool = p.pool; e.bw = p.bw;
+        e.leaky = p.leaky; e.has_post = p.post_scale != nullptr;
+        const int n_t = p.n_t, n8 = n_t >> 3;                       // n_t is a multiple of 16: both halves get n8/2 groups of 8
+        const int g_lo = half * (n8 >> 1);
+        // x16 TMEM loads per warp, plus one x8 load (n_t = 80: 2 x 16 + 8 per warp); timing experiments: 8 = first chunk
+        // only, 32 = barrier handshake only, 16 = no global stores
+        const int n_full = (p.exp_flags & 32) ? 0 : ((p.exp_flags & 8) ? 1 : (n8 >> 2));
+        const bool tail8 = ((n8 >> 1) & 1) && !(p.exp_flags & (8 | 32));
+        const bool nostore = (p.exp_flags & 16) != 0;
+        const int in_h = p.in_h, in_w = p.in_w, os = p.os, n_tiles = p.n_tiles;
         const int m = q * 32 + lane;
         const int xl = m % p.bw, yl = (m / p.bw) % p.bh, nl = m / (p.bw * p.bh);
+        const int oh_ = e.pool ? in_h >> 1 : in_h * os, ow_ = e.pool ? in_w >> 1 : in_w * os;
         int acc = 0; uint32_t acc_phase = 0;
+        unsigned long long c_wt = 0, c_work = 0; DbgClock clk; clk.start(dbg_on && leader && lane == 0 && warp == 2);
         for (int tile = item0; tile < total; tile += item_step) {
-            const TileCoord t = decode_tile(p, tile, m_units, per_unit, rank);
+            const TileCoord t = decode(tile);
             const int n = t.n0 + nl, y = t.y0 + yl, x = t.x0 + xl;
-            const bool valid = n < p.n_tiles;
-            int oh, ow, oy, ox; bool writer = valid;
-            if (p.pool) { oh = p.in_h >> 1; ow = p.in_w >> 1; oy = y >> 1; ox = x >> 1; writer = valid && !(y & 1) && !(x & 1); }
-            else if (p.os == 2) { oh = p.in_h * 2; ow = p.in_w * 2; oy = 2 * y + (t.phase >> 1); ox = 2 * x + (t.phase & 1); }
-            else { oh = p.in_h; ow = p.in_w; oy = y; ox = x; }
-            const int64_t opix = ((int64_t)n * oh + oy) * ow + ox;
-            // narrow fp32 source (raw input channels of lu0.conv2 / the legacy 1x1 shortcut): its taps in registers
-            float xs[(SKT > 0 ? SKT : 1) * (SKIPC > 0 ? SKIPC : 1)];
-            if (SKIPC > 0) {
-#pragma unroll
-                for (int tp = 0; tp < SKT; ++tp) {
-                    const TcTap tap = p.skip_taps[tp];
-                    const int yy = y + tap.dy, xx = x + tap.dx;
-                    const bool inb = valid && yy >= 0 && yy < p.in_h && xx >= 0 && xx < p.in_w;
-#pragma unroll
-                    for (int cs = 0; cs < SKIPC; ++cs)
-                        xs[tp * SKIPC + cs] = inb ? __ldg(p.skip_src + (((int64_t)n * p.in_h + yy) * p.in_w + xx) * SKIPC + cs) : 0.f;
-                }
-            }
+            const bool valid = n < n_tiles && !nostore;
+            int oy, ox; bool writer = valid;
+            if (e.pool) { oy = y >> 1; ox = x >> 1; writer = valid && !(y & 1) && !(x & 1); }
+            else if (os == 2) { oy = 2 * y + (t.phase >> 1); ox = 2 * x + (t.phase & 1); }
+            else { oy = y; ox = x; }
+            const int64_t opix = ((int64_t)n * oh_ + oy) * ow_ + ox;
+            const int co0 = t.n_idx * n_t + g_lo * 8;              // first output channel of this warp's columns
+            float* of = e.out_f + opix * e.cout + co0;              // only dereferenced when the base is non-null
+            __half* oh = e.out_h + opix * e.out_cs + co0;
+            float xs = 0.f;
+            if (SKIPC > 0 && valid) xs = __ldg(p.skip_src + ((int64_t)n * in_h + y) * in_w + x);
             float z[4] = {0.f, 0.f, 0.f, 0.f};           // fused lt logits
+            clk.lap(c_work);
             mbar_wait(tfull0 + 8 * acc, acc_phase);
+            clk.lap(c_wt);
             tc_fence_after();
-            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
-            uint32_t rn[16];                                   // TMEM load of the next chunk is in flight while this one is processed
-            if (c_lo < c_hi) tmem_ld16_issue(tbase + c_lo * 16, rn);
-            for (int c16 = c_lo; c16 < c_hi; ++c16) {
-                uint32_t r[16];
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride) + (uint32_t)(g_lo * 8);
+            // the TMEM load of the next chunk is in flight while the current one is processed
+            uint32_t ra[16], rb[16], rt[8];
+            if (n_full > 0) tmem_ld16_issue(tbase, ra); else if (tail8) tmem_ld8_issue(tbase, rt);
+            for (int i = 0; i < n_full; i += 2) {
                 tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) r[j] = rn[j];
-                if (c16 + 1 < c_hi) tmem_ld16_issue(tbase + (c16 + 1) * 16, rn);
-                const int co = t.n_idx * p.n_t + c16 * 16;
-                float v[16];
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                    const float4 b = *reinterpret_cast<const float4*>(s_bias + co + j4 * 4);
-                    v[j4 * 4 + 0] = __uint_as_float(r[j4 * 4 + 0]) + b.x; v[j4 * 4 + 1] = __uint_as_float(r[j4 * 4 + 1]) + b.y;
-                    v[j4 * 4 + 2] = __uint_as_float(r[j4 * 4 + 2]) + b.z; v[j4 * 4 + 3] = __uint_as_float(r[j4 * 4 + 3]) + b.w;
+                if (i + 1 < n_full) tmem_ld16_issue(tbase + (i + 1) * 16, rb); else if (tail8) tmem_ld8_issue(tbase + n_full * 16, rt);
+                epi_chunk<16, SKIPC, TOPK>(e, ra, co0 + i * 16, xs, writer, of + i * 16, oh + i * 16, z);
+                __syncwarp();        // reconverge before the next .sync.aligned TMEM instruction
+                if (i + 1 < n_full) {
+                    tmem_ld_wait();
+                    if (i + 2 < n_full) tmem_ld16_issue(tbase + (i + 2) * 16, ra); else if (tail8) tmem_ld8_issue(tbase + n_full * 16, rt);
+                    epi_chunk<16, SKIPC, TOPK>(e, rb, co0 + (i + 1) * 16, xs, writer, of + (i + 1) * 16, oh + (i + 1) * 16, z);
+                    __syncwarp();
                 }
-                if (SKIPC > 0) {
-#pragma unroll
-                    for (int tp = 0; tp < SKT; ++tp) {
-#pragma unroll
-                        for (int cs = 0; cs < SKIPC; ++cs) {
-                            const float xv = xs[tp * SKIPC + cs];
-                            const float4* w4 = reinterpret_cast<const float4*>(s_skipw + (tp * SKIPC + cs) * cpad + co);
-#pragma unroll
-                            for (int j4 = 0; j4 < 4; ++j4) {
-                                const float4 w = w4[j4];
-                                v[j4 * 4 + 0] = fmaf(xv, w.x, v[j4 * 4 + 0]); v[j4 * 4 + 1] = fmaf(xv, w.y, v[j4 * 4 + 1]);
-                                v[j4 * 4 + 2] = fmaf(xv, w.z, v[j4 * 4 + 2]); v[j4 * 4 + 3] = fmaf(xv, w.w, v[j4 * 4 + 3]);
-                            }
-                        }
-                    }
-                }
-                if (p.act == ACT_LEAKY) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * p.leaky);       // leaky slope < 1
-                } else if (p.act == ACT_RELU) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-                }
-                if (p.post_scale) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], s_ps[co + j], s_pt[co + j]);
-                }
-                if (p.top_w) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float* wk = s_topw + (co + j) * p.top_k;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (k < p.top_k) z[k] = fmaf(v[j], wk[k], z[k]);
-                    }
-                }
-                if (p.pool) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
-                        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], p.bw));
-                    }
-                }
-#pragma unroll
-                for (int h8 = 0; h8 < 2; ++h8) {
-                    const int c = co + h8 * 8;
-                    if (!writer) continue;
-                    if (p.out_f && c < p.cout) {
-                        float* of = p.out_f + opix * p.cout + c;
-                        if (c + 8 <= p.cout && !(p.cout & 3)) {
-                            reinterpret_cast<float4*>(of)[0] = make_float4(v[h8 * 8 + 0], v[h8 * 8 + 1], v[h8 * 8 + 2], v[h8 * 8 + 3]);
-                            reinterpret_cast<float4*>(of)[1] = make_float4(v[h8 * 8 + 4], v[h8 * 8 + 5], v[h8 * 8 + 6], v[h8 * 8 + 7]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) if (c + j < p.cout) of[j] = v[h8 * 8 + j];
-                        }
-                    }
-                    if (p.out_h && c < p.out_cs) {       // storage channels are padded to a multiple of 8; pad lanes hold 0
-                        __half2 hi[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) hi[j] = __floats2half2_rn(v[h8 * 8 + 2 * j], v[h8 * 8 + 2 * j + 1]);
-                        __half* o = p.out_h + opix * p.out_cs + c;
-                        *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(hi);
-                        if (p.out_planes == 2) {
-                            __half2 lo[4];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float2 f = __half22float2(hi[j]);
-                                lo[j] = __floats2half2_rn(v[h8 * 8 + 2 * j] - f.x, v[h8 * 8 + 2 * j + 1] - f.y);
-                            }
-                            *reinterpret_cast<uint4*>(o + p.out_plane_elems) = *reinterpret_cast<uint4*>(lo);
-                        }
-                    }
-                }
-                __syncwarp();        // reconverge before the next .sync.aligned TMEM load
             }
-            if (p.top_w) {
+            if (tail8) {
+                tmem_ld_wait();
+                epi_chunk<8, SKIPC, TOPK>(e, rt, co0 + n_full * 16, xs, writer, of + n_full * 16, oh + n_full * 16, z);
+                __syncwarp();
+            }
+            if (TOPK > 0) {
                 // the two warps of a lane quarter hold the two column halves of each pixel: combine the partial logits
-                float* zs = s_z + ((size_t)acc * 128 + m) * 4;
-                if (half == 1) { zs[0] = z[0]; zs[1] = z[1]; zs[2] = z[2]; zs[3] = z[3]; }
+                float4* zs = reinterpret_cast<float4*>(s_z) + (acc * 128 + m);
+                if (half == 1) *zs = make_float4(z[0], z[1], z[2], z[3]);
                 asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-                if (half == 0) { z[0] += zs[0]; z[1] += zs[1]; z[2] += zs[2]; z[3] += zs[3]; }
-            }
-            if (p.top_w && writer && half == 0) {
-                float mx = -INFINITY, sum = 0.f;
+                if (half == 0 && writer) {
+                    const float4 o = *zs;
+                    z[0] += o.x; z[1] += o.y; z[2] += o.z; z[3] += o.w;
+                    float mx = -INFINITY, sum = 0.f;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) if (k < p.top_k) { z[k] += s_topb[k]; mx = fmaxf(mx, z[k]); }
+                    for (int k = 0; k < TOPK; ++k) { z[k] += s_topb[k]; mx = fmaxf(mx, z[k]); }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) if (k < p.top_k) { z[k] = expf(z[k] - mx); sum += z[k]; }
-                const float inv = 1.f / sum;
+                    for (int k = 0; k < TOPK; ++k) { z[k] = expf(z[k] - mx); sum += z[k]; }
+                    const float inv = 1.f / sum;
+                    float* pr = p.top_probs + opix * TOPK;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) if (k < p.top_k) p.top_probs[opix * p.top_k + k] = z[k] * inv;
+                    for (int k = 0; k < TOPK; ++k) pr[k] = z[k] * inv;
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty0 + 8 * acc); else mbar_arrive(tempty0 + 8 * acc); }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        clk.lap(c_work);
+        if (clk.on) { atomicAdd(p.dbg + 8, c_wt); atomicAdd(p.dbg + 9, c_work); }
     }
     tc_fence_before();
     __syncthreads();
@@ -640,7 +735,7 @@ EncodeTiledFn encode_fn() {
 
 size_t tc_conv_fixed_bytes(const TcConvParams& p) {
     const size_t cpad = (size_t)p.n_ntiles * p.n_t;
-    const size_t tables = ((size_t)(p.skip_src ? p.skip_ntaps : 0) * p.skip_c * cpad + (p.top_w ? cpad * p.top_k + 4 + 2 * 128 * 4 : 0) + cpad * (p.post_scale ? 3 : 1) + 8) * sizeof(float);
+    const size_t tables = (cpad * ((p.post_scale ? 3 : 1) + (p.skip_src ? 1 : 0) + (p.top_w ? 4 : 0)) + 4 + (p.top_w ? 2 * 128 * 4 : 0) + 8) * sizeof(float);
     return (2 * (size_t)(p.stages + (p.halo ? p.b_stages : 0)) + 4) * 8 + 16 + tables + 1024;
 }
 size_t tc_conv_a_bytes(const TcConvParams& p) {
@@ -653,30 +748,30 @@ size_t tc_conv_smem_bytes(const TcConvParams& p) {
     return p.stages * (size_t)(p.kslab > 0 ? p.kslab : 1) * (tc_conv_a_bytes(p) + tc_conv_b_bytes(p)) + tc_conv_fixed_bytes(p);
 }
 
-template <int SKIPC, int SKT, bool PAIR, bool HALO>
+template <int SKIPC, int TOPK, bool PAIR, bool HALO>
 static cudaError_t configure_one() {
-    return cudaFuncSetAttribute(tc_conv_kernel<SKIPC, SKT, PAIR, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return cudaFuncSetAttribute(tc_conv_kernel<SKIPC, TOPK, PAIR, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
-template <int SKIPC, int SKT>
-static cudaError_t configure_skip() {
-    cudaError_t e = configure_one<SKIPC, SKT, false, false>();
-    if (e == cudaSuccess) e = configure_one<SKIPC, SKT, true, false>();
-    if (e == cudaSuccess) e = configure_one<SKIPC, SKT, false, true>();
-    if (e == cudaSuccess) e = configure_one<SKIPC, SKT, true, true>();
+template <int SKIPC, int TOPK>
+static cudaError_t configure_epi() {
+    cudaError_t e = configure_one<SKIPC, TOPK, false, false>();
+    if (e == cudaSuccess) e = configure_one<SKIPC, TOPK, true, false>();
+    if (e == cudaSuccess) e = configure_one<SKIPC, TOPK, false, true>();
+    if (e == cudaSuccess) e = configure_one<SKIPC, TOPK, true, true>();
     return e;
 }
 
 cudaError_t tc_conv_configure() {
-    cudaError_t e = configure_skip<0, 0>();
-    if (e == cudaSuccess) e = configure_skip<1, 1>();
-    if (e == cudaSuccess) e = configure_skip<1, 9>();
-    if (e == cudaSuccess) e = configure_skip<2, 9>();
-    if (e == cudaSuccess) e = configure_skip<1, 25>();
+    cudaError_t e = configure_epi<0, 0>();
+    if (e == cudaSuccess) e = configure_epi<1, 0>();
+    if (e == cudaSuccess) e = configure_epi<0, 2>();
+    if (e == cudaSuccess) e = configure_epi<0, 3>();
+    if (e == cudaSuccess) e = configure_epi<0, 4>();
     return e;
 }
 
-template <int SKIPC, int SKT, bool PAIR, bool HALO>
+template <int SKIPC, int TOPK, bool PAIR, bool HALO>
 static cudaError_t launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcConvParams& p,
                               int grid, size_t smem, cudaStream_t s) {
     cudaLaunchConfig_t cfg = {};
@@ -685,14 +780,14 @@ static cudaError_t launch_one(const CUtensorMap& a0, const CUtensorMap& a1, cons
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, tc_conv_kernel<SKIPC, SKT, PAIR, HALO>, a0, a1, b, p);
+    return cudaLaunchKernelEx(&cfg, tc_conv_kernel<SKIPC, TOPK, PAIR, HALO>, a0, a1, b, p);
 }
 
-template <int SKIPC, int SKT>
-static cudaError_t launch_skip(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcConvParams& p,
-                               int grid, size_t smem, cudaStream_t s) {
-    if (p.pair) return p.halo ? launch_one<SKIPC, SKT, true, true>(a0, a1, b, p, grid, smem, s) : launch_one<SKIPC, SKT, true, false>(a0, a1, b, p, grid, smem, s);
-    return p.halo ? launch_one<SKIPC, SKT, false, true>(a0, a1, b, p, grid, smem, s) : launch_one<SKIPC, SKT, false, false>(a0, a1, b, p, grid, smem, s);
+template <int SKIPC, int TOPK>
+static cudaError_t launch_epi(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcConvParams& p,
+                              int grid, size_t smem, cudaStream_t s) {
+    if (p.pair) return p.halo ? launch_one<SKIPC, TOPK, true, true>(a0, a1, b, p, grid, smem, s) : launch_one<SKIPC, TOPK, true, false>(a0, a1, b, p, grid, smem, s);
+    return p.halo ? launch_one<SKIPC, TOPK, false, true>(a0, a1, b, p, grid, smem, s) : launch_one<SKIPC, TOPK, false, false>(a0, a1, b, p, grid, smem, s);
 }
 
 cudaError_t launch_tc_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcConvParams& p,
@@ -707,12 +802,13 @@ cudaError_t launch_tc_conv(const CUtensorMap& a0, const CUtensorMap& a1, const C
     size_t smem = tc_conv_smem_bytes(p);
     if (smem < 120 * 1024) smem = 120 * 1024;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    const int skipc = p.skip_src ? p.skip_c : 0, skt = p.skip_src ? p.skip_ntaps : 0;
-    if (skipc == 0) return launch_skip<0, 0>(a0, a1, b, p, grid, smem, s);
-    if (skipc == 1 && skt == 1) return launch_skip<1, 1>(a0, a1, b, p, grid, smem, s);
-    if (skipc == 1 && skt == 9) return launch_skip<1, 9>(a0, a1, b, p, grid, smem, s);
-    if (skipc == 2 && skt == 9) return launch_skip<2, 9>(a0, a1, b, p, grid, smem, s);
-    if (skipc == 1 && skt == 25) return launch_skip<1, 25>(a0, a1, b, p, grid, smem, s);
+    const bool skip = p.skip_src != nullptr;
+    if (skip && (p.skip_c != 1 || p.top_w)) return cudaErrorInvalidValue;
+    if (skip) return launch_epi<1, 0>(a0, a1, b, p, grid, smem, s);
+    if (!p.top_w) return launch_epi<0, 0>(a0, a1, b, p, grid, smem, s);
+    if (p.top_k == 2) return launch_epi<0, 2>(a0, a1, b, p, grid, smem, s);
+    if (p.top_k == 3) return launch_epi<0, 3>(a0, a1, b, p, grid, smem, s);
+    if (p.top_k == 4) return launch_epi<0, 4>(a0, a1, b, p, grid, smem, s);
     return cudaErrorInvalidValue;
 }
 

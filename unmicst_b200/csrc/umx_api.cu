@@ -314,38 +314,82 @@ int build_plan(umx_handle* h) {
     return UMX_OK;
 }
 
-enum { TC_NONE = 0, TC_PLAIN = 1, TC_SKIP_CONCAT = 2, TC_SHORT_SKIP = 3, TC_SHORT_A1 = 4 };
+enum { TC_NONE = 0, TC_PLAIN = 1, TC_SHORT_SKIP = 3, TC_SHORT_A1 = 4 };
 
-bool skip_combo_ok(int c, int ntaps) {       // (channels, taps) combinations instantiated in kernels_tc.cu
-    return (c == 1 && (ntaps == 1 || ntaps == 9 || ntaps == 25)) || (c == 2 && ntaps == 9);
-}
-
-// Which tensor-path form (if any) can run this op.
-//  - lu0.conv2 pattern: concat(raw input with <= 2 channels, wide up tensor): the wide part runs on the tensor
-//    cores, the narrow part is a handful of fp32 FMAs per output in the epilogue (TC_SKIP_CONCAT)
-//  - legacy down layer: k x k conv of the chain + 1x1 shortcut of the layer input (UnMicst.py:91-99): the shortcut
-//    is either folded into the epilogue (1-channel input, TC_SHORT_SKIP) or joins the K loop at the centre tap
+// Which tensor-path form (if any) can run this op (after rewrite_narrow_sources).
+//  - one term: k x k conv / conv-transpose of one or two wide concat sources (TC_PLAIN); k = 1 is the tap-expanded
+//    first layer
+//  - two terms, the second a 1x1 conv of another buffer (legacy shortcut UnMicst.py:95-97, or the tap-expanded raw
+//    input of lu0.conv2): a one-channel source is folded into the epilogue (TC_SHORT_SKIP), a wide one joins the
+//    K loop at the centre tap (TC_SHORT_A1)
 int tc_mode_of(const umx_handle* h, const Op& op) {
     if (h->precision == UMX_PREC_FP32 || op.kind != OP_CONV) return TC_NONE;
     const ConvSpec& sp = op.spec;
     const TermHost& T0 = sp.terms[0];
-    if (T0.k != 3 && T0.k != 5) return TC_NONE;
-    if (sp.transpose && sp.terms.size() != 1) return TC_NONE;
+    if (T0.k != 1 && T0.k != 3 && T0.k != 5) return TC_NONE;
+    if (sp.transpose && (sp.terms.size() != 1 || T0.k == 1)) return TC_NONE;
     const Buffer& a = h->bufs[T0.src0];
-    if (a.h < 4 || a.w < 4) return TC_NONE;
-    if (sp.terms.size() == 1) {
-        if (T0.src1 >= 0 && a.c <= 2 && !sp.transpose && !sp.pool && h->bufs[T0.src1].c >= 8 && skip_combo_ok(a.c, T0.k * T0.k))
-            return TC_SKIP_CONCAT;
-        return a.c >= 8 ? TC_PLAIN : TC_NONE;
-    }
+    if (a.h < 4 || a.w < 4 || a.c < 8) return TC_NONE;
+    if (T0.src1 >= 0 && h->bufs[T0.src1].c < 8) return TC_NONE;
+    if (sp.terms.size() == 1) return TC_PLAIN;
     if (sp.terms.size() == 2) {
         const TermHost& T1 = sp.terms[1];
-        if (T1.k != 1 || T1.src1 >= 0 || T0.src1 >= 0 || a.c < 8) return TC_NONE;
+        if (T1.k != 1 || T1.src1 >= 0 || T0.src1 >= 0 || T0.k == 1) return TC_NONE;
         const Buffer& sc = h->bufs[T1.src0];
         if (sc.c >= 8) return TC_SHORT_A1;
-        return skip_combo_ok(sc.c, 1) ? TC_SHORT_SKIP : TC_NONE;
+        return sc.c == 1 ? TC_SHORT_SKIP : TC_NONE;
     }
     return TC_NONE;
+}
+
+// Tensor-path form of the convolutions that read the raw network input (1-2 channels, too narrow for a TMA box):
+// the input is expanded once per tile into a k*k*C-channel fp16 "taps" buffer (im2col of the SAME-padded tile,
+// channel = tap*C + c) by taps_kernel; then
+//   first layer  conv_k(input)            ->  1x1 conv of the taps buffer (K = k*k*C)
+//   lu0.conv2    conv_k(concat(input,up)) ->  conv_k(up) + 1x1 conv of the taps buffer at the centre tap
+// which are the same linear maps with the same weights (HWIO rows [tap][c] are already in taps-channel order).
+int rewrite_narrow_sources(umx_handle* h) {
+    if (h->precision == UMX_PREC_FP32) return UMX_OK;
+    std::map<std::pair<int, int>, int> taps_of;       // (source buffer, k) -> taps buffer
+    std::vector<Op> ops;
+    auto taps_buffer = [&](int src, int k) {
+        auto key = std::make_pair(src, k);
+        auto it = taps_of.find(key);
+        if (it != taps_of.end()) return it->second;
+        const Buffer sb = h->bufs[src];
+        const int tb = new_buffer(h, sb.name + ".taps" + std::to_string(k), sb.h, sb.w, k * k * sb.c);
+        Op op; op.kind = OP_TAPS; op.name = h->bufs[tb].name; op.out_buf = tb; op.taps_src = src; op.taps_k = k;
+        op.flops_per_tile = 0;
+        op.bytes_per_tile = (double)sb.h * sb.w * (4.0 * sb.c + 4.0 * k * k * sb.c);
+        ops.push_back(op);
+        taps_of[key] = tb;
+        return tb;
+    };
+    for (auto& op : h->ops) {
+        if (op.kind == OP_CONV && !op.spec.transpose && op.spec.terms.size() == 1) {
+            TermHost& T = op.spec.terms[0];
+            const Buffer& a = h->bufs[T.src0];
+            const bool narrow = a.c <= 2 && (T.k == 3 || T.k == 5) && a.h >= 4 && a.w >= 4;
+            if (narrow && T.src1 < 0) {
+                T.src0 = taps_buffer(T.src0, T.k);
+                T.k = 1;                                   // [tap][c][cout] is already [1][tap*C + c][cout]
+            } else if (narrow && h->bufs[T.src1].c >= 8) {
+                const int sc = a.c, wc = h->bufs[T.src1].c, taps = T.k * T.k, cout = op.spec.cout;
+                TermHost t1; t1.k = 1; t1.src0 = taps_buffer(T.src0, T.k);
+                t1.w.resize((size_t)taps * sc * cout);
+                std::vector<float> w0((size_t)taps * wc * cout);
+                for (int t = 0; t < taps; ++t) {
+                    memcpy(&t1.w[(size_t)t * sc * cout], &T.w[(size_t)t * (sc + wc) * cout], (size_t)sc * cout * sizeof(float));
+                    memcpy(&w0[(size_t)t * wc * cout], &T.w[((size_t)t * (sc + wc) + sc) * cout], (size_t)wc * cout * sizeof(float));
+                }
+                T.w = w0; T.src0 = T.src1; T.src1 = -1;
+                op.spec.terms.push_back(t1);
+            }
+        }
+        ops.push_back(std::move(op));
+    }
+    h->ops = std::move(ops);
+    return UMX_OK;
 }
 
 int pick_n_tile(int cout) {
@@ -436,11 +480,11 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     memset(&tp, 0, sizeof(tp));
     const TermHost& T = sp.terms[0];
     const int mode = op.tc_mode, k = T.k, ntaps_w = k * k;
-    const Buffer& a0 = h->bufs[mode == TC_SKIP_CONCAT ? T.src1 : T.src0];
+    const Buffer& a0 = h->bufs[T.src0];
     const Buffer* a1 = nullptr;
     if (mode == TC_PLAIN && T.src1 >= 0) a1 = &h->bufs[T.src1];
     if (mode == TC_SHORT_A1) a1 = &h->bufs[sp.terms[1].src0];
-    const Buffer* narrow = mode == TC_SKIP_CONCAT ? &h->bufs[T.src0] : (mode == TC_SHORT_SKIP ? &h->bufs[sp.terms[1].src0] : nullptr);
+    const Buffer* narrow = mode == TC_SHORT_SKIP ? &h->bufs[sp.terms[1].src0] : nullptr;
     const int planes = h->precision == UMX_PREC_SINGLE ? 1 : 2;
     tp.in_h = a0.h; tp.in_w = a0.w;
     tp.bw = std::min(a0.w, 16); tp.bh = std::min(a0.h, 128 / tp.bw); tp.bn = 128 / (tp.bw * tp.bh);
@@ -452,8 +496,21 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     ConvTerm tt; memset(&tt, 0, sizeof(tt));
     if (sp.transpose) convt_taps(&tt, k); else conv_taps(&tt, k);
     for (int ph = 0; ph < tp.nphase; ++ph) {
-        tp.ntaps[ph] = tt.ntaps[ph];
-        for (int i = 0; i < tt.ntaps[ph]; ++i) tp.taps[ph][i] = TcTap{tt.dy[ph][i], tt.dx[ph][i], tt.wi[ph][i], 0};
+        TcPhaseGrid& g = tp.grid[ph];
+        const int nt = tt.ntaps[ph];
+        int nx = 1;
+        while (nx < nt && tt.dy[ph][nx] == tt.dy[ph][0]) ++nx;
+        g.ntaps = nt; g.nx = nx; g.dy0 = tt.dy[ph][0]; g.dx0 = tt.dx[ph][0]; g.wi0 = tt.wi[ph][0];
+        g.dstep = nx > 1 ? tt.dx[ph][1] - tt.dx[ph][0] : (nt > nx ? tt.dy[ph][nx] - tt.dy[ph][0] : 1);
+        g.wix = nx > 1 ? tt.wi[ph][1] - tt.wi[ph][0] : 0;
+        g.wiy = nt > nx ? tt.wi[ph][nx] - tt.wi[ph][0] : 0;
+        for (int i = 0; i < nt; ++i) {          // the tap list must be exactly this grid
+            const int iy = i / nx, ix = i % nx;
+            if (nt % nx || tt.dy[ph][i] != g.dy0 + g.dstep * iy || tt.dx[ph][i] != g.dx0 + g.dstep * ix ||
+                tt.wi[ph][i] != g.wi0 + iy * g.wiy + ix * g.wix) {
+                set_error("%s: taps of phase %d are not a regular grid", op.name.c_str(), ph); return UMX_EINVAL;
+            }
+        }
     }
     tp.planes = planes;
     {
@@ -464,27 +521,32 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     // (instead of once per tap), cutting the L2->SM traffic of A by ~k*k/1.4
     {
         const char* e = getenv("UMX_TC_HALO");
-        if ((e ? atoi(e) : 1) && a0.w >= 16 && a0.h >= 16) {
+        if ((e ? atoi(e) : 1) && a0.w >= 16 && a0.h >= 16 && ntaps_w > 1) {
             tp.halo = 1; tp.bw = 8; tp.bh = 16; tp.bn = 1;
             tp.hx0 = tt.hx0; tp.hy0 = tt.hy0;
             tp.pw = tp.bw + tt.hx0 + tt.hx1; tp.ph = tp.bh + tt.hy0 + tt.hy1;
         }
     }
-    const int skip_c = narrow ? narrow->c : 0;
-    const int skip_nt = mode == TC_SKIP_CONCAT ? ntaps_w : (mode == TC_SHORT_SKIP ? 1 : 0);
     {
         const size_t cpad = (size_t)tp.n_ntiles * tp.n_t;
-        const size_t tables = (size_t)skip_nt * skip_c * cpad * 4 + (op.fuse_top >= 0 ? (cpad * h->K + 8 + 2 * 128 * 4) * 4 : 0)
-                              + cpad * (sp.has_post ? 3 : 1) * 4 + 64;
+        const size_t tables = (cpad * ((sp.has_post ? 3 : 1) + (narrow ? 1 : 0) + (op.fuse_top >= 0 ? 4 : 0)) + 4 +
+                               (op.fuse_top >= 0 ? 2 * 128 * 4 : 0) + 8) * 4 + 64;
         const size_t budget = 227 * 1024 - 2048 - 512 - tables;
         const size_t bb = tc_conv_b_bytes(tp);
         if (tp.halo) {
             const size_t ab = tc_conv_a_bytes(tp);
             tp.stages = 2;
-            tp.gb = 3;
+            if (const char* e = getenv("UMX_TC_ASTAGES")) tp.stages = std::max(2, std::min(8, atoi(e)));
+            // taps per weight slot: as many as still leave three slots in flight (every slot costs a barrier round trip
+            // and a tcgen05.commit in the single issuing thread, so few large slots beat many small ones)
+            int max_taps = 1;
+            for (int ph = 0; ph < tp.nphase; ++ph) max_taps = std::max(max_taps, (int)tp.grid[ph].ntaps);
+            tp.gb = std::min(9, max_taps);
+            while (tp.gb > 1 && budget < tp.stages * ab + 3 * (size_t)tp.gb * bb) tp.gb--;
             if (const char* e = getenv("UMX_TC_GB")) tp.gb = std::max(1, std::min(9, atoi(e)));
-            while (tp.gb > 1 && budget < 2 * ab + 2 * (size_t)tp.gb * bb) tp.gb--;
-            tp.b_stages = budget > 2 * ab ? (int)std::min<size_t>(6, (budget - 2 * ab) / ((size_t)tp.gb * bb)) : 0;
+            while (tp.stages > 2 && budget < tp.stages * ab + 2 * (size_t)tp.gb * bb) tp.stages--;
+            while (tp.gb > 1 && budget < tp.stages * ab + 2 * (size_t)tp.gb * bb) tp.gb--;
+            tp.b_stages = budget > tp.stages * ab ? (int)std::min<size_t>(6, (budget - tp.stages * ab) / ((size_t)tp.gb * bb)) : 0;
             if (tp.b_stages < 2) { tp.halo = 0; tp.bw = std::min(a0.w, 16); tp.bh = std::min(a0.h, 128 / tp.bw); tp.bn = 128 / (tp.bw * tp.bh); }
         }
         tp.kslab = 1;
@@ -525,28 +587,15 @@ int lower_conv_tc(umx_handle* h, Op& op) {
         const int r0 = a0.c, r1 = a1 ? a1->c : 0;
         put_rows(T.w, ntaps_w, r0 + r1, 0, r0, 0, 0);
         if (r1) put_rows(T.w, ntaps_w, r0 + r1, r0, r1, tp.c0, 0);
-    } else if (mode == TC_SKIP_CONCAT) {
-        put_rows(T.w, ntaps_w, skip_c + a0.c, skip_c, a0.c, 0, 0);
     } else if (mode == TC_SHORT_SKIP) {
         put_rows(T.w, ntaps_w, a0.c, 0, a0.c, 0, 0);
     } else {    // TC_SHORT_A1: the 1x1 shortcut's rows live at the centre tap only
         put_rows(T.w, ntaps_w, a0.c, 0, a0.c, 0, 0);
         put_rows(sp.terms[1].w, 1, a1->c, 0, a1->c, tp.c0, tp.center_tap);
     }
-    if (narrow) {
-        std::vector<float> wskip((size_t)skip_nt * skip_c * sp.cout);
-        if (mode == TC_SKIP_CONCAT) {
-            const int ctot = skip_c + a0.c;
-            for (int t = 0; t < ntaps_w; ++t)
-                for (int i = 0; i < skip_c; ++i)
-                    memcpy(&wskip[((size_t)t * skip_c + i) * sp.cout], &T.w[((size_t)t * ctot + i) * sp.cout], sp.cout * sizeof(float));
-            for (int t = 0; t < ntaps_w; ++t) tp.skip_taps[t] = tp.taps[0][t];
-        } else {
-            wskip = sp.terms[1].w;
-            tp.skip_taps[0] = TcTap{0, 0, 0, 0};
-        }
-        UMX_TRY(upload(h, wskip, &d));
-        tp.skip_w = d; tp.skip_c = skip_c; tp.skip_ntaps = skip_nt; tp.skip_src = narrow->d;
+    if (narrow) {       // one-channel 1x1 shortcut: weights [1][1][cout]
+        UMX_TRY(upload(h, sp.terms[1].w, &d));
+        tp.skip_w = d; tp.skip_c = 1; tp.skip_src = narrow->d;
         if (!narrow->d) { set_error("%s: fp32 skip source missing", op.name.c_str()); return UMX_EINVAL; }
     }
     if (op.fuse_top >= 0) {
@@ -583,7 +632,6 @@ int lower_plan(umx_handle* h) {
         Op& op = h->ops[i];
         op.tc_mode = tc_mode_of(h, op);
         op.use_tc = op.tc_mode != TC_NONE;
-        op.skip_mode = op.tc_mode == TC_SKIP_CONCAT;
         op.use_first = !op.use_tc && first_eligible(h, op);
     }
     // lt 1x1 conv + softmax rides in the epilogue of the conv that feeds it when one CTA tile spans all channels
@@ -604,13 +652,15 @@ int lower_plan(umx_handle* h) {
         if (op.kind == OP_CONV) {
             for (size_t ti = 0; ti < op.spec.terms.size(); ++ti) {
                 const TermHost& t = op.spec.terms[ti];
-                if (op.tc_mode == TC_SKIP_CONCAT) { h->bufs[t.src0].need_f = true; h->bufs[t.src1].need_h = true; continue; }
                 if (op.tc_mode == TC_SHORT_SKIP && ti == 1) { h->bufs[t.src0].need_f = true; continue; }
                 for (int s : {t.src0, t.src1}) {
                     if (s < 0) continue;
                     if (op.use_tc) h->bufs[s].need_h = true; else h->bufs[s].need_f = true;
                 }
             }
+        } else if (op.kind == OP_TAPS) {
+            h->bufs[op.taps_src].need_f = true;
+            h->bufs[op.out_buf].need_h = true;
         } else if (!op.fused_away) {
             h->bufs[op.top_src].need_f = true;
         }
@@ -632,6 +682,12 @@ int lower_plan(umx_handle* h) {
             else if (op.use_first) UMX_TRY(lower_conv_first(h, op));
             else UMX_TRY(lower_conv_simt(h, op));
             op.spec = ConvSpec();       // host copies of the weights are no longer needed
+        } else if (op.kind == OP_TAPS) {
+            const Buffer& sb = h->bufs[op.taps_src];
+            const Buffer& ob = h->bufs[op.out_buf];
+            op.taps.src = sb.d; op.taps.out = ob.dh; op.taps.out_plane_elems = ob.plane_elems; op.taps.out_planes = ob.planes;
+            op.taps.S = sb.h; op.taps.cin = sb.c; op.taps.ks = op.taps_k; op.taps.cs = ob.cs();
+            op.bytes_per_tile = (double)sb.h * sb.w * (4.0 * sb.c + 2.0 * ob.planes * ob.cs());
         } else if (!op.fused_away) {
             float* d = nullptr;
             UMX_TRY(upload(h, op.top_w, &d)); op.tp.w = d;
@@ -693,7 +749,21 @@ int run_network(umx_handle* h, int nb, float* probs_out) {
             TcConvParams tp = op.tcp;
             tp.n_tiles = nb;
             if (op.fuse_top >= 0) tp.top_probs = probs_out;
+            if (tp.exp_flags & 64) {           // UMX_TC_EXP=64: per-role cycle accounting, printed per launch (debug only)
+                if (!h->d_dbg) UMX_CUDA_TRY(cudaMalloc(&h->d_dbg, 16 * sizeof(unsigned long long)));
+                UMX_CUDA_TRY(cudaMemsetAsync(h->d_dbg, 0, 16 * sizeof(unsigned long long), h->stream));
+                tp.dbg = h->d_dbg;
+            }
             UMX_CUDA_TRY(launch_tc_conv(op.mapA0, op.mapA1, op.mapB, tp, h->num_sms, h->stream));
+            if (tp.exp_flags & 64) {
+                unsigned long long c[16];
+                UMX_CUDA_TRY(cudaMemcpyAsync(c, h->d_dbg, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+                UMX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+                const double n = c[15] ? (double)c[15] : 1.0;      // MMA-issuing CTAs
+                fprintf(stderr, "[umx dbg] %-14s tiles %5d halo %d pair %d stages %d/%d gb %d | producer waitA %.0f waitB %.0f work %.0f | mma waitT %.0f waitA %.0f waitB %.0f work %.0f | epi waitT %.0f work %.0f (kcycles per issuing CTA)\n",
+                        op.name.c_str(), nb, tp.halo, tp.pair, tp.stages, tp.b_stages, tp.gb, c[0] / n / 1e3, c[1] / n / 1e3, c[2] / n / 1e3,
+                        c[4] / n / 1e3, c[5] / n / 1e3, c[6] / n / 1e3, c[7] / n / 1e3, c[8] / n / 1e3, c[9] / n / 1e3);
+            }
         } else if (op.kind == OP_CONV && op.use_first) {
             FirstParams fp = op.fp;
             fp.n_tiles = nb;
@@ -702,6 +772,10 @@ int run_network(umx_handle* h, int nb, float* probs_out) {
             ConvParams cp = op.cp;
             cp.n_tiles = nb;
             UMX_CUDA_TRY(launch_conv_simt(cp, h->stream));
+        } else if (op.kind == OP_TAPS) {
+            TapsParams tp = op.taps;
+            tp.n_tiles = nb;
+            UMX_CUDA_TRY(launch_taps(tp, h->stream));
         } else {
             TopParams tp = op.tp;
             tp.n_pix = (int64_t)nb * h->S * h->S;
@@ -819,6 +893,8 @@ int umx_create(const umx_model_desc* desc, const umx_tensor* weights, int32_t n_
     h->num_sms = prop.multiProcessorCount;
     h->precision = desc->precision == UMX_PREC_DEFAULT ? UMX_PREC_SPLIT3 : desc->precision;
     if (h->precision < UMX_PREC_FP32 || h->precision > UMX_PREC_SINGLE) { set_error("unknown precision %d", desc->precision); umx_destroy(h); return UMX_EINVAL; }
+    rc = rewrite_narrow_sources(h);
+    if (rc != UMX_OK) { umx_destroy(h); return rc; }
     int64_t per_tile = 0;
     for (auto& b : h->bufs) per_tile += b.per_tile() * 4;
     per_tile += (int64_t)S * S * h->K * 4;
@@ -856,6 +932,7 @@ void umx_destroy(umx_handle* h) {
     for (auto p : h->dev_allocs) cudaFree(p);
     for (auto& b : h->bufs) { if (b.d) cudaFree(b.d); if (b.dh) cudaFree(b.dh); }
     if (h->probs) cudaFree(h->probs);
+    if (h->d_dbg) cudaFree(h->d_dbg);
     if (h->d_img) cudaFree(h->d_img);
     if (h->d_probs_rows) cudaFree(h->d_probs_rows);
     for (int i = 0; i < 2; ++i) {

@@ -66,7 +66,7 @@ struct ConvSpec {
     int act = 0;
 };
 
-enum OpKind { OP_CONV = 0, OP_TOP = 1 };
+enum OpKind { OP_CONV = 0, OP_TOP = 1, OP_TAPS = 2 };
 
 struct Op {
     OpKind kind = OP_CONV;
@@ -75,17 +75,17 @@ struct Op {
     bool use_tc = false;
     bool use_first = false;          // dedicated first-layer kernel (1-2 input channels, 3x3, pooled)
     FirstParams fp{};
-    // how the tensor path maps the op: 1 plain (one or two wide concat sources), 2 narrow first concat source folded
-    // into the epilogue, 3 two terms with a narrow 1x1 shortcut in the epilogue, 4 two terms with a wide 1x1
-    // shortcut joining the K loop at the centre tap
+    // how the tensor path maps the op: 1 plain (one or two wide concat sources), 3 two terms with a one-channel 1x1
+    // shortcut in the epilogue, 4 two terms with a wide 1x1 term joining the K loop at the centre tap
     int tc_mode = 0;
-    bool skip_mode = false;          // tc_mode == 2
     int fuse_top = -1;               // index of the OP_TOP fused into this conv's epilogue
     bool fused_away = false;         // OP_TOP executed inside the preceding conv
     ConvParams cp{};                 // fp32 CUDA-core implementation
     TcConvParams tcp{};              // tcgen05 implementation
     alignas(64) CUtensorMap mapA0, mapA1, mapB;
     TopParams tp{};
+    TapsParams taps{};               // OP_TAPS: k x k tap expansion of a narrow buffer
+    int taps_src = -1, taps_k = 0;
     std::vector<float> top_w, top_b;
     int top_src = -1;
     int out_buf = -1;
@@ -131,6 +131,7 @@ struct umx_handle {
     float* d_stage_f32[2] = {nullptr, nullptr}; size_t d_stage_f32_bytes = 0;
     cudaEvent_t ev_stitch[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    unsigned long long* d_dbg = nullptr;         // UMX_TC_EXP=64 cycle counters
     // profiling
     bool profiling = false;
     std::vector<umx::ProfSlot> prof;

@@ -67,6 +67,14 @@ struct FirstParams {
     int32_t out_cs;             // channel stride of out_h (cout rounded up to 8)
 };
 
+struct TapsParams {             // k x k tap expansion (im2col of the SAME-padded tile) of a 1-2 channel fp32 buffer
+    const float* src;           // [n][S][S][cin]
+    __half* out;                // fp16 hi[/lo] planes [planes][n][S][S][cs], channel = tap*cin + c, pad channels 0
+    int64_t out_plane_elems;
+    int32_t out_planes;
+    int32_t n_tiles, S, cin, ks, cs;
+};
+
 struct TopParams {              // lt 1x1 conv (+ folded BN) + softmax over K classes
     const float* src;           // [n_pix][cin]
     const float* w;             // [cin][K]
@@ -115,6 +123,7 @@ struct StitchParams {           // PI2D.patchOutput/getValidOutput as a gather +
 cudaError_t launch_conv_simt(const ConvParams& p, cudaStream_t s);
 cudaError_t launch_top_softmax(const TopParams& p, cudaStream_t s);
 cudaError_t launch_first_conv(const FirstParams& p, cudaStream_t s);
+cudaError_t launch_taps(const TapsParams& p, cudaStream_t s);
 size_t first_conv_smem_bytes(int cin, int ks, int cout);
 cudaError_t launch_gather_tiles(const GatherParams& p, cudaStream_t s);
 cudaError_t launch_stitch(const StitchParams& p, cudaStream_t s);

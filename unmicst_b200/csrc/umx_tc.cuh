@@ -7,7 +7,10 @@
 
 namespace umx {
 
-struct TcTap { int8_t dy, dx, wi, pad; };
+// The taps of one output phase form an ny x nx grid with constant steps, so the kernels walk them with adds instead
+// of table look-ups: tap (iy, ix) reads the input at (dy0 + dstep*iy, dx0 + dstep*ix) and the weight tap
+// wi0 + iy*wiy + ix*wix.  conv k x k: one phase, dstep +1; stride-2 conv-transpose: four sub-pixel phases, dstep -1.
+struct TcPhaseGrid { int32_t ntaps, nx, dy0, dx0, dstep, wi0, wiy, wix; };
 
 struct TcConvParams {
     int32_t n_tiles;             // image tiles in this launch
@@ -18,21 +21,21 @@ struct TcConvParams {
     int32_t n_t;                 // GEMM N per CTA tile (multiple of 16, <= 256)
     int32_t n_ntiles;            // ceil(cout / n_t)
     int32_t nphase, os;          // conv: 1,1   conv-transpose: 4,2
-    int32_t ntaps[4];
-    TcTap   taps[4][25];         // per phase: input offset and weight tap (conv 3x3/5x5: 1 phase; conv-transpose: 4 phases, <= 9 taps)
+    TcPhaseGrid grid[4];         // per phase tap grid (conv 3x3/5x5: 1 phase; conv-transpose: 4 phases, <= 9 taps)
     int32_t planes;              // 1: fp16 operands, 1 MMA/product; 2: hi/lo split, 3 MMAs/product
     int32_t stages;              // smem pipeline depth (halo mode: patch slots)
     int32_t halo;                // 1: one (bh+halo) x (bw+halo) pixel patch per 64-channel slab serves every tap
     int32_t pw, ph, hx0, hy0;    // patch size and left/top halo (halo mode)
     int32_t b_stages, gb;        // halo mode: weight ring depth, taps per weight slot
     int32_t kslab;               // plain mode: 64-channel slabs per ring slot (more MMAs per barrier round trip)
-    int32_t exp_flags;           // timing experiments only (results invalid): 1 no A loads, 2 no B loads, 4 one MMA per stage, 8 no epilogue math
+    int32_t exp_flags;           // timing experiments only (results invalid): 1 no TMA loads, 4 one MMA per slab, 8 first epilogue chunk only, 16 no global stores, 32 no epilogue work
+    unsigned long long* dbg;     // exp_flags & 64: 16 cycle counters (producer / MMA / epilogue waits and work), else nullptr
     int32_t pair;                // 1: CTA pairs, tcgen05.mma.cta_group::2 (M = 256 across two SMs)
     int32_t act;                 // umx::Act
     float   leaky;
     int32_t pool;                // fused 2x2 max-pool (conv only)
     int32_t a1_center;           // 1: the second source is a 1x1 shortcut: its slabs join the K loop at the centre tap only
-    int32_t center_tap;          // index of the (0,0) tap in taps[0]
+    int32_t center_tap;          // linear index (= weight tap) of the (0,0) tap of a k x k conv
     const float* bias;           // [cout] or nullptr
     const float* post_scale;     // [cout] affine applied after the activation (legacy: batch-norm follows the ReLU) or nullptr
     const float* post_shift;
@@ -41,12 +44,10 @@ struct TcConvParams {
     int32_t out_planes;          // planes to write into out_h (1 or 2)
     int32_t out_cs;              // channel stride of out_h (cout rounded up to 8; pad channels are written as 0)
     float*  out_f;               // fp32 [n][oh][ow][cout] or nullptr
-    // narrow skip source handled in fp32 in the epilogue (raw input channels of lu0.conv2)
-    const float* skip_src;       // [n][in_h][in_w][skip_c] or nullptr
-    const float* skip_w;         // [skip_ntaps][skip_c][cout] fp32 (BN scale folded)
-    int32_t skip_c;
-    int32_t skip_ntaps;          // 1 (1x1 shortcut), 9 or 25 (k x k taps of a concat source)
-    TcTap   skip_taps[25];
+    // one-channel fp32 source entering as a 1x1 shortcut in the epilogue (legacy down layers)
+    const float* skip_src;       // [n][in_h][in_w] or nullptr
+    const float* skip_w;         // [cout] fp32
+    int32_t skip_c;              // 1 when skip_src is set
     // fused lt 1x1 conv + softmax (replaces the activation store when top_w != nullptr)
     const float* top_w;          // [cout][K]
     const float* top_b;          // [K] or nullptr
