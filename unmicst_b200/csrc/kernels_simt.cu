@@ -255,6 +255,26 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const FirstParams p) {
         for (int b = 0; b < NB; ++b)
 #pragma unroll
             for (int ci = 0; ci < CIN; ++ci) in[a][b][ci] = xin[((2 * py + a) * PW + 2 * px + b) * CIN + ci];
+    if (p.taps_out) {
+        // tap expansion of this thread's 2x2 pixels for the tensor-path consumer (lu0.conv2): channel = tap*CIN + c
+        constexpr int NCH = KS * KS * CIN;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int64_t pix = ((int64_t)n * p.S + y0 + 2 * py + (q >> 1)) * p.S + x0 + 2 * px + (q & 1);
+            __half* o = p.taps_out + pix * p.taps_cs;
+#pragma unroll
+            for (int g = 0; g < (NCH + 7) / 8; ++g) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int ch = g * 8 + j;
+                    v[j] = ch < NCH ? in[(q >> 1) + (ch / CIN) / KS][(q & 1) + (ch / CIN) % KS][ch % CIN] : 0.f;
+                }
+                store_h2x4(o + g * 8, p.taps_plane_elems, p.taps_planes, v);
+                store_h2x4(o + g * 8 + 4, p.taps_plane_elems, p.taps_planes, v + 4);
+            }
+        }
+    }
     const int oh = p.pool ? p.S / 2 : p.S;
     for (int cg = 0; cg < cpad; cg += 16) {
         float acc[4][16];

@@ -24,7 +24,9 @@ namespace umx {
 
 namespace {
 
-constexpr int kThreads = 320;               // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int kEpiWarps = 8;                 // epilogue warps: kEpiSub per TMEM lane quarter, each a share of the N columns
+constexpr int kEpiSub = kEpiWarps / 4;
+constexpr int kThreads = 64 + 32 * kEpiWarps; // warp 0 TMA, warp 1 MMA, then the epilogue warps
 constexpr int kAPlaneBytes = 128 * 128;       // 128 rows x 64 fp16
 constexpr int kAccStride = 256;               // TMEM columns between the two accumulator stages
 constexpr uint32_t kSpinLimit = 1u << 28;     // trap instead of hanging the GPU on a pipeline bug
@@ -389,7 +391,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if (lane == 0) {
             for (int s = 0; s < n_stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
             for (int s = 0; s < nb_stages; ++s) { mbar_init(fullB0 + 8 * s, 1); mbar_init(emptyB0 + 8 * s, 1); }
-            for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, PAIR ? 16 : 8); }
+            for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, (PAIR ? 2 : 1) * kEpiWarps); }
             fence_barrier_init();
         }
         __syncwarp();
@@ -617,20 +619,22 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             if (dbg_on) { atomicAdd(p.dbg + 4, c_wt); atomicAdd(p.dbg + 5, c_wa); atomicAdd(p.dbg + 6, c_wb); atomicAdd(p.dbg + 7, c_work); atomicAdd(p.dbg + 15, 1ull); }
         }
     } else {
-        // ================= epilogue (8 warps: two per TMEM lane quarter, each half of the N columns) =================
+        // ================= epilogue (kEpiWarps warps: kEpiSub per TMEM lane quarter, each a share of the N columns) =================
         const int q = warp & 3;                                     // TMEM lane quarter this warp may read
-        const int half = (warp - 2) >> 2;                           // which half of the N columns it handles
+        const int sub = (warp - 2) >> 2;                            // which share of the N columns it handles
         EpiCtx e;
         e.s_bias = s_bias; e.s_ps = s_ps; e.s_pt = s_pt; e.s_skipw = s_skipw; e.s_topw4 = reinterpret_cast<const float4*>(s_topw);
         e.out_f = p.out_f; e.out_h = p.out_h; e.out_plane_elems = p.out_plane_elems;
         e.cout = p.cout; e.out_cs = p.out_cs; e.out_planes = p.out_planes; e.act = p.act; e.pool = p.pool; e.bw = p.bw;
         e.leaky = p.leaky; e.has_post = p.post_scale != nullptr;
-        const int n_t = p.n_t, n8 = n_t >> 3;                       // n_t is a multiple of 16: both halves get n8/2 groups of 8
-        const int g_lo = half * (n8 >> 1);
-        // x16 TMEM loads per warp, plus one x8 load (n_t = 80: 2 x 16 + 8 per warp); timing experiments: 8 = first chunk
+        // the N tile is dealt out in groups of 8 columns (16-byte fp16 stores): n_t = 80 -> 3, 3, 2, 2 groups
+        const int n_t = p.n_t, n8 = n_t >> 3;
+        const int g_lo = sub * (n8 / kEpiSub) + min(sub, n8 % kEpiSub);
+        const int g_n = n8 / kEpiSub + (sub < n8 % kEpiSub ? 1 : 0);
+        // x16 TMEM loads per warp, plus one x8 load for an odd group count; timing experiments: 8 = first chunk
         // only, 32 = barrier handshake only, 16 = no global stores
-        const int n_full = (p.exp_flags & 32) ? 0 : ((p.exp_flags & 8) ? 1 : (n8 >> 2));
-        const bool tail8 = ((n8 >> 1) & 1) && !(p.exp_flags & (8 | 32));
+        const int n_full = (p.exp_flags & 32) ? 0 : ((p.exp_flags & 8) ? min(1, g_n >> 1) : (g_n >> 1));
+        const bool tail8 = (g_n & 1) && !(p.exp_flags & (8 | 32));
         const bool nostore = (p.exp_flags & 16) != 0;
         const int in_h = p.in_h, in_w = p.in_w, os = p.os, n_tiles = p.n_tiles;
         const int m = q * 32 + lane;
@@ -679,13 +683,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 __syncwarp();
             }
             if (TOPK > 0) {
-                // the two warps of a lane quarter hold the two column halves of each pixel: combine the partial logits
-                float4* zs = reinterpret_cast<float4*>(s_z) + (acc * 128 + m);
-                if (half == 1) *zs = make_float4(z[0], z[1], z[2], z[3]);
-                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-                if (half == 0 && writer) {
-                    const float4 o = *zs;
-                    z[0] += o.x; z[1] += o.y; z[2] += o.z; z[3] += o.w;
+                // the warps of a lane quarter hold the column shares of each pixel: combine the partial logits
+                float4* zs = reinterpret_cast<float4*>(s_z) + (acc * (kEpiSub - 1) * 128 + m);
+                if (sub > 0) zs[(sub - 1) * 128] = make_float4(z[0], z[1], z[2], z[3]);
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(32 * kEpiSub) : "memory");
+                if (sub == 0 && writer) {
+#pragma unroll
+                    for (int o_ = 0; o_ < kEpiSub - 1; ++o_) {
+                        const float4 o = zs[o_ * 128];
+                        z[0] += o.x; z[1] += o.y; z[2] += o.z; z[3] += o.w;
+                    }
                     float mx = -INFINITY, sum = 0.f;
 #pragma unroll
                     for (int k = 0; k < TOPK; ++k) { z[k] += s_topb[k]; mx = fmaxf(mx, z[k]); }
@@ -735,7 +742,7 @@ EncodeTiledFn encode_fn() {
 
 size_t tc_conv_fixed_bytes(const TcConvParams& p) {
     const size_t cpad = (size_t)p.n_ntiles * p.n_t;
-    const size_t tables = (cpad * ((p.post_scale ? 3 : 1) + (p.skip_src ? 1 : 0) + (p.top_w ? 4 : 0)) + 4 + (p.top_w ? 2 * 128 * 4 : 0) + 8) * sizeof(float);
+    const size_t tables = (cpad * ((p.post_scale ? 3 : 1) + (p.skip_src ? 1 : 0) + (p.top_w ? 4 : 0)) + 4 + (p.top_w ? 2 * (kEpiSub - 1) * 128 * 4 : 0) + 8) * sizeof(float);
     return (2 * (size_t)(p.stages + (p.halo ? p.b_stages : 0)) + 4) * 8 + 16 + tables + 1024;
 }
 size_t tc_conv_a_bytes(const TcConvParams& p) {

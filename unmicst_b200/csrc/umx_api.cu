@@ -348,6 +348,8 @@ int tc_mode_of(const umx_handle* h, const Op& op) {
 //   first layer  conv_k(input)            ->  1x1 conv of the taps buffer (K = k*k*C)
 //   lu0.conv2    conv_k(concat(input,up)) ->  conv_k(up) + 1x1 conv of the taps buffer at the centre tap
 // which are the same linear maps with the same weights (HWIO rows [tap][c] are already in taps-channel order).
+bool first_eligible(const umx_handle* h, const Op& op);
+
 int rewrite_narrow_sources(umx_handle* h) {
     if (h->precision == UMX_PREC_FP32) return UMX_OK;
     std::map<std::pair<int, int>, int> taps_of;       // (source buffer, k) -> taps buffer
@@ -371,8 +373,10 @@ int rewrite_narrow_sources(umx_handle* h) {
             const Buffer& a = h->bufs[T.src0];
             const bool narrow = a.c <= 2 && (T.k == 3 || T.k == 5) && a.h >= 4 && a.w >= 4;
             if (narrow && T.src1 < 0) {
-                T.src0 = taps_buffer(T.src0, T.k);
-                T.k = 1;                                   // [tap][c][cout] is already [1][tap*C + c][cout]
+                if (!first_eligible(h, op)) {              // (the fp32 first-layer kernel is faster when it applies: K = k*k*C is tiny)
+                    T.src0 = taps_buffer(T.src0, T.k);
+                    T.k = 1;                               // [tap][c][cout] is already [1][tap*C + c][cout]
+                }
             } else if (narrow && h->bufs[T.src1].c >= 8) {
                 const int sc = a.c, wc = h->bufs[T.src1].c, taps = T.k * T.k, cout = op.spec.cout;
                 TermHost t1; t1.k = 1; t1.src0 = taps_buffer(T.src0, T.k);
@@ -530,12 +534,12 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     {
         const size_t cpad = (size_t)tp.n_ntiles * tp.n_t;
         const size_t tables = (cpad * ((sp.has_post ? 3 : 1) + (narrow ? 1 : 0) + (op.fuse_top >= 0 ? 4 : 0)) + 4 +
-                               (op.fuse_top >= 0 ? 2 * 128 * 4 : 0) + 8) * 4 + 64;
+                               (op.fuse_top >= 0 ? 2 * 3 * 128 * 4 : 0) + 8) * 4 + 64;
         const size_t budget = 227 * 1024 - 2048 - 512 - tables;
         const size_t bb = tc_conv_b_bytes(tp);
         if (tp.halo) {
             const size_t ab = tc_conv_a_bytes(tp);
-            tp.stages = 2;
+            tp.stages = 3;          // patch slots: the next slab's patch is in flight while this one is multiplied
             if (const char* e = getenv("UMX_TC_ASTAGES")) tp.stages = std::max(2, std::min(8, atoi(e)));
             // taps per weight slot: as many as still leave three slots in flight (every slot costs a barrier round trip
             // and a tcgen05.commit in the single issuing thread, so few large slots beat many small ones)
@@ -697,6 +701,19 @@ int lower_plan(umx_handle* h) {
         ProfSlot ps; ps.name = op.name;
         op.prof_slot = (int)h->prof.size();
         h->prof.push_back(ps);
+    }
+    // the first-layer kernel already holds every input patch in registers: let it write the tap expansion too
+    for (auto& t : h->ops) {
+        if (t.kind != OP_TAPS) continue;
+        for (auto& f : h->ops) {
+            if (f.kind != OP_CONV || !f.use_first || f.fp.src != t.taps.src || f.fp.ks != t.taps.ks || f.fp.cin != t.taps.cin) continue;
+            f.fp.taps_out = t.taps.out; f.fp.taps_plane_elems = t.taps.out_plane_elems;
+            f.fp.taps_planes = t.taps.out_planes; f.fp.taps_cs = t.taps.cs;
+            f.bytes_per_tile += t.bytes_per_tile;
+            f.name += "+taps"; h->prof[f.prof_slot].name = f.name;
+            t.fused_away = true;
+            break;
+        }
     }
     return UMX_OK;
 }

@@ -65,6 +65,10 @@ struct FirstParams {
     int64_t out_plane_elems;
     int32_t out_planes;
     int32_t out_cs;             // channel stride of out_h (cout rounded up to 8)
+    // optional second output: the k x k tap expansion of the input (see TapsParams), written from the same patch
+    __half* taps_out;           // fp16 hi[/lo] planes [planes][n][S][S][taps_cs] or nullptr
+    int64_t taps_plane_elems;
+    int32_t taps_planes, taps_cs;
 };
 
 struct TapsParams {             // k x k tap expansion (im2col of the SAME-padded tile) of a 1-2 channel fp32 buffer
