@@ -59,6 +59,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or ~the hint elapses)
+// instead of spinning through the issue slots; for waits that are not on the critical path (epilogue, producer).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(ns) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+        if (++spins > (kSpinLimit >> 4)) { printf("umx tc_conv: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
@@ -430,48 +447,56 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const uint32_t txA = (PAIR ? 2u : 1u) * (uint32_t)(planes * a_box_bytes);
                 int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
                 unsigned long long c_wa = 0, c_wb = 0, c_work = 0; DbgClock clk; clk.start(dbg_on);
+                const uint32_t txB = (PAIR ? 2u : 1u) * (uint32_t)(gb * b_bytes);      // a weight box always carries gb taps
+                // Patch loads run n_stages - 1 slabs ahead of the weight loads of the same (item, slab) stream: the
+                // slot they wait for was released by a slab whose weights have already been requested.
+                int a_tile = item0, a_cb = 0;
+                TileCoord ta = decode(a_tile);
+                auto issue_a = [&]() {
+                    const bool second = a_cb >= nch0;
+                    const int cc = (second ? a_cb - nch0 : a_cb) * 64;
+                    const CUtensorMap* mapA = second ? &mapA1 : &mapA0;
+                    clk.lap(c_work);
+                    mbar_wait(empty0 + 8 * sa, pa ^ 1);
+                    clk.lap(c_wa);
+                    const uint32_t fa = full0 + 8 * sa;
+                    const uint32_t da = smem_u32(smem) + (uint32_t)(sa * stage_bytes);
+                    if (noload) { if (leader) mbar_arrive(fa); }
+                    else if (leader) mbar_expect_tx(fa, txA);
+                    for (int pl = 0; pl < planes && !noload; ++pl) {
+                        if (PAIR) tma_load_5d_pair(da + pl * a_plane_bytes, mapA, fa, cc, ta.x0 - hx0, ta.y0 - hy0, ta.n0, pl);
+                        else tma_load_5d(da + pl * a_plane_bytes, mapA, fa, cc, ta.x0 - hx0, ta.y0 - hy0, ta.n0, pl);
+                    }
+                    if (++sa == n_stages) { sa = 0; pa ^= 1; }
+                    if (++a_cb == n_chunks) { a_cb = 0; a_tile += item_step; if (a_tile < total) ta = decode(a_tile); }
+                };
+                for (int i = 0; i < n_stages - 1 && a_tile < total; ++i) issue_a();
                 for (int tile = item0; tile < total; tile += item_step) {
                     const TileCoord t = decode(tile);
                     const TcPhaseGrid g = p.grid[t.phase];
                     const int ncol = t.n_idx * n_t + (PAIR ? rank * (n_t / 2) : 0);
-                    const int ax = t.x0 - hx0, ay = t.y0 - hy0;
                     for (int cb = 0; cb < n_chunks; ++cb) {
                         const bool second = cb >= nch0;
                         const int cc = (second ? cb - nch0 : cb) * 64;
-                        const CUtensorMap* mapA = second ? &mapA1 : &mapA0;
-                        clk.lap(c_work);
-                        mbar_wait(empty0 + 8 * sa, pa ^ 1);
-                        clk.lap(c_wa);
-                        const uint32_t fa = full0 + 8 * sa;
-                        const uint32_t da = smem_u32(smem) + (uint32_t)(sa * stage_bytes);
-                        if (noload) { if (leader) mbar_arrive(fa); }
-                        else if (leader) mbar_expect_tx(fa, txA);
-                        for (int pl = 0; pl < planes && !noload; ++pl) {
-                            if (PAIR) tma_load_5d_pair(da + pl * a_plane_bytes, mapA, fa, cc, ax, ay, t.n0, pl);
-                            else tma_load_5d(da + pl * a_plane_bytes, mapA, fa, cc, ax, ay, t.n0, pl);
-                        }
-                        if (++sa == n_stages) { sa = 0; pa ^= 1; }
                         const bool centre_only = second && a1c;        // 1x1 term: its slabs exist at the centre tap only
                         const int te = centre_only ? 1 : g.ntaps;
                         const int kc = (second ? c0s : 0) + cc;
-                        int wi = centre_only ? ctap : g.wi0, ix = 0;
+                        const int wi0 = centre_only ? ctap : g.wi0;
                         for (int t0 = 0; t0 < te; t0 += gb) {
-                            const int ng = min(gb, te - t0);
                             clk.lap(c_work);
                             mbar_wait(emptyB0 + 8 * sb, pb ^ 1);
                             clk.lap(c_wb);
                             const uint32_t fb = fullB0 + 8 * sb;
-                            uint32_t db = smem_u32(smem_b) + (uint32_t)(sb * gb * b_bytes);
+                            const uint32_t db = smem_u32(smem_b) + (uint32_t)(sb * gb * b_bytes);
                             if (noload) { if (leader) mbar_arrive(fb); }
-                            else if (leader) mbar_expect_tx(fb, (PAIR ? 2u : 1u) * (uint32_t)(ng * b_bytes));
-                            for (int j = 0; j < ng && !noload; ++j, db += b_bytes) {
-                                if (PAIR) tma_load_4d_pair(db, &mapB, fb, kc, ncol, wi, 0);
-                                else tma_load_4d(db, &mapB, fb, kc, ncol, wi, 0);
-                                wi += g.wix;
-                                if (++ix == g.nx) { ix = 0; wi += g.wiy - g.nx * g.wix; }
+                            else {
+                                if (leader) mbar_expect_tx(fb, txB);
+                                if (PAIR) tma_load_4d_pair(db, &mapB, fb, kc, ncol, wi0 + t0, 0);
+                                else tma_load_4d(db, &mapB, fb, kc, ncol, wi0 + t0, 0);
                             }
                             if (++sb == nb_stages) { sb = 0; pb ^= 1; }
                         }
+                        if (a_tile < total) issue_a();     // after this slab's weights: the MMA thread is never kept waiting for them
                     }
                 }
                 clk.lap(c_work);
@@ -533,7 +558,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             if constexpr (HALO) {
                 const int pw = p.pw, hx0 = p.hx0, hy0 = p.hy0, n_chunks = nch0 + nch1;
                 const uint32_t a_hi = desc_hi((uint32_t)pw * 128u);     // consecutive 8-pixel rows are one patch row apart
-                const uint32_t b16 = (uint32_t)b_bytes >> 4;
+                const uint32_t b16 = b_plane16;                        // weight slot = [plane][tap][rows]: taps one plane tile apart
+                const uint32_t bp16 = (uint32_t)gb * b_plane16;
                 int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
                 for (int tile = item0; tile < total; tile += item_step) {
                     const TcPhaseGrid g = p.grid[decode(tile).phase];
@@ -566,7 +592,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             tc_fence_after();
                             uint32_t b_lo = desc_lo(smem_u32(smem_b) + (uint32_t)(sb * gb * b_bytes));
                             for (int j = 0; j < ng; ++j, b_lo += b16) {
-                                umma_slab<PAIR>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, nk, split, a_plane16, b_plane16, accumulate, exp_mma);
+                                umma_slab<PAIR>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, nk, split, a_plane16, bp16, accumulate, exp_mma);
                                 a_lo += sx;
                                 if (++ix == g.nx) { ix = 0; a_lo += row_back; }
                             }
@@ -658,7 +684,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             if (SKIPC > 0 && valid) xs = __ldg(p.skip_src + ((int64_t)n * in_h + y) * in_w + x);
             float z[4] = {0.f, 0.f, 0.f, 0.f};           // fused lt logits
             clk.lap(c_work);
-            mbar_wait(tfull0 + 8 * acc, acc_phase);
+            mbar_wait_relaxed(tfull0 + 8 * acc, acc_phase);
             clk.lap(c_wt);
             tc_fence_after();
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride) + (uint32_t)(g_lo * 8);
@@ -834,12 +860,12 @@ int make_act_tensor_map(CUtensorMap* out, const __half* base, int planes, int64_
 }
 
 int make_weight_tensor_map(CUtensorMap* out, const __half* base, int planes, int taps, int cout, int cin, int n_t,
-                           int box_planes) {
+                           int box_planes, int box_taps) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return -1;
     cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)taps, (cuuint64_t)planes};
     cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)cout * cin * 2, (cuuint64_t)taps * cout * cin * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)n_t, 1, (cuuint32_t)box_planes};
+    cuuint32_t box[4] = {64, (cuuint32_t)n_t, (cuuint32_t)box_taps, (cuuint32_t)box_planes};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), dims, strides, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

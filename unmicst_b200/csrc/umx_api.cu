@@ -608,13 +608,28 @@ int lower_conv_tc(umx_handle* h, Op& op) {
         if (!top.top_b.empty()) { UMX_TRY(upload(h, top.top_b, &d)); tp.top_b = d; }
         tp.top_k = h->K;
     }
+    // Device tap order = phase by phase (the taps of a phase are contiguous, so halo mode fetches a whole group of
+    // taps with one TMA box), followed by `gb` all-zero taps so a box that starts at the last tap never leaves the tensor.
+    std::vector<int> order;
+    for (int ph = 0; ph < tp.nphase; ++ph) {
+        TcPhaseGrid& g = tp.grid[ph];
+        const int start = (int)order.size();
+        for (int i = 0; i < g.ntaps; ++i) order.push_back(g.wi0 + (i / g.nx) * g.wiy + (i % g.nx) * g.wix);
+        g.wi0 = start; g.wix = 1; g.wiy = g.nx;
+    }
+    if ((int)order.size() != ntaps_w) { set_error("%s: phases do not cover every weight tap once", op.name.c_str()); return UMX_EINVAL; }
+    const int box_taps = tp.halo ? tp.gb : 1, taps_dev = ntaps_w + (tp.halo ? tp.gb : 0);
+    std::vector<float> wperm((size_t)taps_dev * cin * sp.cout, 0.f);
+    for (int i = 0; i < ntaps_w; ++i)
+        memcpy(&wperm[(size_t)i * cin * sp.cout], &wmain[(size_t)order[i] * cin * sp.cout], (size_t)cin * sp.cout * sizeof(float));
+    for (int i = 0; i < ntaps_w; ++i) if (order[i] == tp.center_tap) { tp.center_tap = i; break; }
     std::vector<__half> wh;
-    split_weights(wmain, ntaps_w, cin, sp.cout, planes, &wh);
+    split_weights(wperm, taps_dev, cin, sp.cout, planes, &wh);
     __half* dw = nullptr;
     UMX_CUDA_TRY(cudaMalloc(&dw, wh.size() * sizeof(__half)));
     h->dev_allocs.push_back(reinterpret_cast<float*>(dw));
     UMX_CUDA_TRY(cudaMemcpy(dw, wh.data(), wh.size() * sizeof(__half), cudaMemcpyHostToDevice));
-    int rc = make_weight_tensor_map(&op.mapB, dw, planes, ntaps_w, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, planes);
+    int rc = make_weight_tensor_map(&op.mapB, dw, planes, taps_dev, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, planes, box_taps);
     if (rc) { set_error("%s: cuTensorMapEncodeTiled(weights) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
     if (!a0.dh || (a1 && !a1->dh)) { set_error("%s: fp16 source buffer missing", op.name.c_str()); return UMX_EINVAL; }
     const int box_w = tp.halo ? tp.pw : tp.bw, box_h = tp.halo ? tp.ph : tp.bh, box_p = tp.halo ? 1 : planes;

@@ -35,7 +35,7 @@ struct TcConvParams {
     float   leaky;
     int32_t pool;                // fused 2x2 max-pool (conv only)
     int32_t a1_center;           // 1: the second source is a 1x1 shortcut: its slabs join the K loop at the centre tap only
-    int32_t center_tap;          // linear index (= weight tap) of the (0,0) tap of a k x k conv
+    int32_t center_tap;          // linear index (= device weight tap) of the (0,0) tap of a k x k conv
     const float* bias;           // [cout] or nullptr
     const float* post_scale;     // [cout] affine applied after the activation (legacy: batch-norm follows the ReLU) or nullptr
     const float* post_shift;
@@ -67,8 +67,8 @@ cudaError_t launch_tc_conv(const CUtensorMap& a0, const CUtensorMap& a1, const C
 // activations: fp16 [planes][n][h][w][c]; box = {64 ch, bw, bh, bn, planes}
 int make_act_tensor_map(CUtensorMap* out, const __half* base, int planes, int64_t plane_elems, int n, int h, int w, int c,
                         int bw, int bh, int bn, int box_planes);
-// weights: fp16 [planes][tap][cout][cin]; box = {64 cin, n_t, 1, planes}
+// weights: fp16 [planes][tap][cout][cin]; box = {64 cin, n_t, box_taps, planes}
 int make_weight_tensor_map(CUtensorMap* out, const __half* base, int planes, int taps, int cout, int cin, int n_t,
-                           int box_planes);
+                           int box_planes, int box_taps);
 
 }  // namespace umx
