@@ -337,10 +337,13 @@ def run_ours(args):
     by_hbm = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9 / peaks["hbm"] if dom["ms"] else 0
     if bound == "tensor" and by_hbm > achieved / peak:      # the binding roofline term is HBM for this layer
         bound, achieved, peak, unit = "hbm", by_hbm * peaks["hbm"], peaks["hbm"], "GB/s"
-    traffic = None
+    traffic = None          # DRAM bytes per launch of the dominant kernel: ncu per-tile figure x this run's tiles per launch
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(dom["name"])
+        ent = json.load(open(tp)).get(dom["name"])
+        if isinstance(ent, dict) and dom["launches"]:
+            my_tiles = (band[1] - max(band[0] - 1, 0)) * npc if band else 0
+            traffic = ent["dram_bytes_per_tile"] * my_tiles / dom["launches"]
     roofline = {"kernel": dom["name"], "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peaks["source"],
                 "avg_launch_ms": dom["ms"] / max(1, dom["launches"]), "share_of_step": dom["ms"] / total_ms,
