@@ -246,6 +246,43 @@ __device__ __forceinline__ void umma_slab(uint32_t tmem_d, uint32_t a_lo, uint32
     }
 }
 
+// Halo mode: the `ng` taps of one weight slot against one patch, as straight-line code for a compile-time number of
+// 16-channel steps (the gap between two MMAs of the single issuing thread must stay below the ~40-50 cycles one
+// N = 80 MMA takes, or the tensor pipe idles at every tap boundary).
+template <bool PAIR, int NK, bool SPLIT>
+__device__ __forceinline__ void halo_taps(int ng, uint32_t tmem_d, uint32_t& a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                          uint32_t idesc, uint32_t a_plane16, uint32_t bp16, uint32_t b16, int sx, int row_back,
+                                          int nx, int& ix, uint32_t& accumulate) {
+    for (int j = 0; j < ng; ++j, b_lo += b16) {
+        umma_issue<PAIR>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+        accumulate = 1;
+        if (SPLIT) {
+            umma_acc<PAIR>(tmem_d, a_lo, a_hi, b_lo + bp16, b_hi, idesc);
+            umma_acc<PAIR>(tmem_d, a_lo + a_plane16, a_hi, b_lo, b_hi, idesc);
+        }
+#pragma unroll
+        for (int k = 1; k < NK; ++k) {
+            umma_acc<PAIR>(tmem_d, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc);
+            if (SPLIT) {
+                umma_acc<PAIR>(tmem_d, a_lo + 2 * k, a_hi, b_lo + bp16 + 2 * k, b_hi, idesc);
+                umma_acc<PAIR>(tmem_d, a_lo + a_plane16 + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc);
+            }
+        }
+        a_lo += sx;
+        if (++ix == nx) { ix = 0; a_lo += row_back; }
+    }
+}
+
+template <bool PAIR, bool SPLIT>
+__device__ __forceinline__ void halo_taps_nk(int nk, int ng, uint32_t tmem_d, uint32_t& a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t a_plane16, uint32_t bp16, uint32_t b16, int sx, int row_back,
+                                             int nx, int& ix, uint32_t& accumulate) {
+    if (nk == 4) halo_taps<PAIR, 4, SPLIT>(ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
+    else if (nk == 1) halo_taps<PAIR, 1, SPLIT>(ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
+    else if (nk == 2) halo_taps<PAIR, 2, SPLIT>(ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
+    else halo_taps<PAIR, 3, SPLIT>(ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
+}
+
 // Everything the epilogue of one accumulator tile needs that does not change from item to item.
 struct EpiCtx {
     const float* s_bias; const float* s_ps; const float* s_pt; const float* s_skipw; const float4* s_topw4;
@@ -470,34 +507,41 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     if (++sa == n_stages) { sa = 0; pa ^= 1; }
                     if (++a_cb == n_chunks) { a_cb = 0; a_tile += item_step; if (a_tile < total) ta = decode(a_tile); }
                 };
-                for (int i = 0; i < n_stages - 1 && a_tile < total; ++i) issue_a();
-                for (int tile = item0; tile < total; tile += item_step) {
-                    const TileCoord t = decode(tile);
-                    const TcPhaseGrid g = p.grid[t.phase];
-                    const int ncol = t.n_idx * n_t + (PAIR ? rank * (n_t / 2) : 0);
-                    for (int cb = 0; cb < n_chunks; ++cb) {
-                        const bool second = cb >= nch0;
-                        const int cc = (second ? cb - nch0 : cb) * 64;
-                        const bool centre_only = second && a1c;        // 1x1 term: its slabs exist at the centre tap only
-                        const int te = centre_only ? 1 : g.ntaps;
-                        const int kc = (second ? c0s : 0) + cc;
-                        const int wi0 = centre_only ? ctap : g.wi0;
-                        for (int t0 = 0; t0 < te; t0 += gb) {
-                            clk.lap(c_work);
-                            mbar_wait(emptyB0 + 8 * sb, pb ^ 1);
-                            clk.lap(c_wb);
-                            const uint32_t fb = fullB0 + 8 * sb;
-                            const uint32_t db = smem_u32(smem_b) + (uint32_t)(sb * gb * b_bytes);
-                            if (noload) { if (leader) mbar_arrive(fb); }
-                            else {
-                                if (leader) mbar_expect_tx(fb, txB);
-                                if (PAIR) tma_load_4d_pair(db, &mapB, fb, kc, ncol, wi0 + t0, 0);
-                                else tma_load_4d(db, &mapB, fb, kc, ncol, wi0 + t0, 0);
-                            }
-                            if (++sb == nb_stages) { sb = 0; pb ^= 1; }
+                // weight loads of one slab (one box per slot of gb taps); they run one slab ahead of the MMA thread
+                int b_tile = item0, b_cb = 0;
+                TileCoord tb = decode(b_tile);
+                auto issue_b = [&]() {
+                    const TcPhaseGrid g = p.grid[tb.phase];
+                    const int ncol = tb.n_idx * n_t + (PAIR ? rank * (n_t / 2) : 0);
+                    const bool second = b_cb >= nch0;
+                    const int cc = (second ? b_cb - nch0 : b_cb) * 64;
+                    const bool centre_only = second && a1c;        // 1x1 term: its slabs exist at the centre tap only
+                    const int te = centre_only ? 1 : g.ntaps;
+                    const int kc = (second ? c0s : 0) + cc;
+                    const int wi0 = centre_only ? ctap : g.wi0;
+                    for (int t0 = 0; t0 < te; t0 += gb) {
+                        clk.lap(c_work);
+                        mbar_wait(emptyB0 + 8 * sb, pb ^ 1);
+                        clk.lap(c_wb);
+                        const uint32_t fb = fullB0 + 8 * sb;
+                        const uint32_t db = smem_u32(smem_b) + (uint32_t)(sb * gb * b_bytes);
+                        if (noload) { if (leader) mbar_arrive(fb); }
+                        else {
+                            if (leader) mbar_expect_tx(fb, txB);
+                            if (PAIR) tma_load_4d_pair(db, &mapB, fb, kc, ncol, wi0 + t0, 0);
+                            else tma_load_4d(db, &mapB, fb, kc, ncol, wi0 + t0, 0);
                         }
-                        if (a_tile < total) issue_a();     // after this slab's weights: the MMA thread is never kept waiting for them
+                        if (++sb == nb_stages) { sb = 0; pb ^= 1; }
                     }
+                    if (++b_cb == n_chunks) { b_cb = 0; b_tile += item_step; if (b_tile < total) tb = decode(b_tile); }
+                };
+                // order per slab s: weights(s+1), then patch(s+n_stages-1): the wait for a free patch slot (= the MMAs of
+                // slab s-1 have retired) never holds back weights the MMA thread needs next
+                for (int i = 0; i < n_stages - 1 && a_tile < total; ++i) issue_a();
+                if (b_tile < total) issue_b();
+                while (b_tile < total) {
+                    issue_b();
+                    if (a_tile < total) issue_a();
                 }
                 clk.lap(c_work);
                 if (dbg_on && leader) { atomicAdd(p.dbg + 0, c_wa); atomicAdd(p.dbg + 1, c_wb); atomicAdd(p.dbg + 2, c_work); }
@@ -590,12 +634,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             mbar_wait(fullB0 + 8 * sb, pb);
                             clk.lap(c_wb);
                             tc_fence_after();
-                            uint32_t b_lo = desc_lo(smem_u32(smem_b) + (uint32_t)(sb * gb * b_bytes));
-                            for (int j = 0; j < ng; ++j, b_lo += b16) {
-                                umma_slab<PAIR>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, nk, split, a_plane16, bp16, accumulate, exp_mma);
-                                a_lo += sx;
-                                if (++ix == g.nx) { ix = 0; a_lo += row_back; }
-                            }
+                            const uint32_t b_lo = desc_lo(smem_u32(smem_b) + (uint32_t)(sb * gb * b_bytes));
+                            if (exp_mma & 128) {}                 // timing experiment: the issue loop without the MMAs
+                            else if (split) halo_taps_nk<PAIR, true>(nk, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, g.nx, ix, accumulate);
+                            else halo_taps_nk<PAIR, false>(nk, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, g.nx, ix, accumulate);
                             if (PAIR) umma_commit_pair(emptyB0 + 8 * sb); else umma_commit(emptyB0 + 8 * sb);
                             if (++sb == nb_stages) { sb = 0; pb ^= 1; }
                         }
