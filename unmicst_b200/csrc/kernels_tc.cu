@@ -290,6 +290,7 @@ struct EpiCtx {
     int cout, out_cs, out_planes, act, pool, bw;
     float leaky;
     bool has_post;
+    bool wide_store;            // fp16-only output whose 16-channel chunks are 32-byte aligned and inside the row
 };
 
 // Bias / shortcut / activation / post-affine of NC accumulator columns of one pixel, then either the fused lt logits
@@ -346,6 +347,26 @@ __device__ __forceinline__ void epi_chunk(const EpiCtx& e, const uint32_t (&r)[N
         }
     }
     if (!writer) return;
+    if (NC == 16 && e.wide_store) {      // fp16 only, 32-byte aligned rows: one 256-bit store per plane
+        __half2 hi[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hi[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+        const uint32_t* h = reinterpret_cast<const uint32_t*>(hi);
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(oh), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]),
+                     "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]) : "memory");
+        if (e.out_planes == 2) {
+            __half2 lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float2 f = __half22float2(hi[j]);
+                lo[j] = __floats2half2_rn(v[2 * j] - f.x, v[2 * j + 1] - f.y);
+            }
+            const uint32_t* l = reinterpret_cast<const uint32_t*>(lo);
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(oh + e.out_plane_elems), "r"(l[0]), "r"(l[1]), "r"(l[2]),
+                         "r"(l[3]), "r"(l[4]), "r"(l[5]), "r"(l[6]), "r"(l[7]) : "memory");
+        }
+        return;
+    }
 #pragma unroll
     for (int h8 = 0; h8 < NC / 8; ++h8) {
         const int c = co + h8 * 8;
@@ -695,14 +716,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         e.out_f = p.out_f; e.out_h = p.out_h; e.out_plane_elems = p.out_plane_elems;
         e.cout = p.cout; e.out_cs = p.out_cs; e.out_planes = p.out_planes; e.act = p.act; e.pool = p.pool; e.bw = p.bw;
         e.leaky = p.leaky; e.has_post = p.post_scale != nullptr;
+        e.wide_store = p.out_f == nullptr && p.out_h != nullptr && (p.out_cs & 15) == 0 && p.n_ntiles * p.n_t <= p.out_cs &&
+                       (p.out_plane_elems & 15) == 0 && !(p.exp_flags & 512);
         // the N tile is dealt out in groups of 8 columns (16-byte fp16 stores): n_t = 80 -> 3, 3, 2, 2 groups
         const int n_t = p.n_t, n8 = n_t >> 3;
         const int g_lo = sub * (n8 / kEpiSub) + min(sub, n8 % kEpiSub);
         const int g_n = n8 / kEpiSub + (sub < n8 % kEpiSub ? 1 : 0);
         // x16 TMEM loads per warp, plus one x8 load for an odd group count; timing experiments: 8 = first chunk
         // only, 32 = barrier handshake only, 16 = no global stores
-        const int n_full = (p.exp_flags & 32) ? 0 : ((p.exp_flags & 8) ? min(1, g_n >> 1) : (g_n >> 1));
-        const bool tail8 = (g_n & 1) && !(p.exp_flags & (8 | 32));
+        const bool noepi = (p.exp_flags & 32) != 0, one_chunk = (p.exp_flags & 8) != 0;
+        const int lead8 = (!noepi && !one_chunk && (g_lo & 1) && g_n > 0) ? 1 : 0;
+        const int n_full = noepi ? 0 : (one_chunk ? min(1, g_n >> 1) : ((g_n - lead8) >> 1));
+        const bool tail8 = ((g_n - lead8) & 1) && !noepi && !one_chunk;
         const bool nostore = (p.exp_flags & 16) != 0;
         const int in_h = p.in_h, in_w = p.in_w, os = p.os, n_tiles = p.n_tiles;
         const int m = q * 32 + lane;
@@ -730,24 +755,35 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             clk.lap(c_wt);
             tc_fence_after();
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride) + (uint32_t)(g_lo * 8);
-            // the TMEM load of the next chunk is in flight while the current one is processed
+            // the TMEM load of the next chunk is in flight while the current one is processed; an odd first group is
+            // taken alone so that every 16-column chunk starts on a 32-byte boundary of the fp16 row (256-bit stores)
             uint32_t ra[16], rb[16], rt[8];
-            if (n_full > 0) tmem_ld16_issue(tbase, ra); else if (tail8) tmem_ld8_issue(tbase, rt);
+            const uint32_t tb16 = tbase + lead8 * 8;
+            const int cb16 = co0 + lead8 * 8;
+            float* of16 = of + lead8 * 8; __half* oh16 = oh + lead8 * 8;
+            if (lead8) tmem_ld8_issue(tbase, rt); else if (n_full > 0) tmem_ld16_issue(tb16, ra); else if (tail8) tmem_ld8_issue(tb16, rt);
+            if (lead8) {
+                tmem_ld_wait();
+                if (n_full > 0) tmem_ld16_issue(tb16, ra);
+                epi_chunk<8, SKIPC, TOPK>(e, rt, co0, xs, writer, of, oh, z);
+                __syncwarp();        // reconverge before the next .sync.aligned TMEM instruction
+                if (n_full == 0 && tail8) tmem_ld8_issue(tb16, rt);
+            }
             for (int i = 0; i < n_full; i += 2) {
                 tmem_ld_wait();
-                if (i + 1 < n_full) tmem_ld16_issue(tbase + (i + 1) * 16, rb); else if (tail8) tmem_ld8_issue(tbase + n_full * 16, rt);
-                epi_chunk<16, SKIPC, TOPK>(e, ra, co0 + i * 16, xs, writer, of + i * 16, oh + i * 16, z);
-                __syncwarp();        // reconverge before the next .sync.aligned TMEM instruction
+                if (i + 1 < n_full) tmem_ld16_issue(tb16 + (i + 1) * 16, rb); else if (tail8) tmem_ld8_issue(tb16 + n_full * 16, rt);
+                epi_chunk<16, SKIPC, TOPK>(e, ra, cb16 + i * 16, xs, writer, of16 + i * 16, oh16 + i * 16, z);
+                __syncwarp();
                 if (i + 1 < n_full) {
                     tmem_ld_wait();
-                    if (i + 2 < n_full) tmem_ld16_issue(tbase + (i + 2) * 16, ra); else if (tail8) tmem_ld8_issue(tbase + n_full * 16, rt);
-                    epi_chunk<16, SKIPC, TOPK>(e, rb, co0 + (i + 1) * 16, xs, writer, of + (i + 1) * 16, oh + (i + 1) * 16, z);
+                    if (i + 2 < n_full) tmem_ld16_issue(tb16 + (i + 2) * 16, ra); else if (tail8) tmem_ld8_issue(tb16 + n_full * 16, rt);
+                    epi_chunk<16, SKIPC, TOPK>(e, rb, cb16 + (i + 1) * 16, xs, writer, of16 + (i + 1) * 16, oh16 + (i + 1) * 16, z);
                     __syncwarp();
                 }
             }
             if (tail8) {
                 tmem_ld_wait();
-                epi_chunk<8, SKIPC, TOPK>(e, rt, co0 + n_full * 16, xs, writer, of + n_full * 16, oh + n_full * 16, z);
+                epi_chunk<8, SKIPC, TOPK>(e, rt, cb16 + n_full * 16, xs, writer, of16 + n_full * 16, oh16 + n_full * 16, z);
                 __syncwarp();
             }
             if (TOPK > 0) {
