@@ -558,11 +558,30 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 };
                 // order per slab s: weights(s+1), then patch(s+n_stages-1): the wait for a free patch slot (= the MMAs of
                 // slab s-1 have retired) never holds back weights the MMA thread needs next
-                for (int i = 0; i < n_stages - 1 && a_tile < total; ++i) issue_a();
-                if (b_tile < total) issue_b();
-                while (b_tile < total) {
-                    issue_b();
-                    if (a_tile < total) issue_a();
+                if (p.b_resident) {
+                    // every weight tile once: one box of all taps per slab, all on the first weight barrier
+                    if (item0 < total) {
+                        if (noload) { if (leader) mbar_arrive(fullB0); }
+                        else {
+                            if (leader) mbar_expect_tx(fullB0, (uint32_t)n_chunks * txB);
+                            const int ncol = PAIR ? rank * (n_t / 2) : 0;
+                            for (int cb = 0; cb < n_chunks; ++cb) {
+                                const bool second = cb >= nch0;
+                                const int kc = (second ? c0s : 0) + (second ? cb - nch0 : cb) * 64;
+                                const uint32_t db = smem_u32(smem_b) + (uint32_t)(cb * gb * b_bytes);
+                                if (PAIR) tma_load_4d_pair(db, &mapB, fullB0, kc, ncol, 0, 0);
+                                else tma_load_4d(db, &mapB, fullB0, kc, ncol, 0, 0);
+                            }
+                        }
+                    }
+                    while (a_tile < total) issue_a();
+                } else {
+                    for (int i = 0; i < n_stages - 1 && a_tile < total; ++i) issue_a();
+                    if (b_tile < total) issue_b();
+                    while (b_tile < total) {
+                        issue_b();
+                        if (a_tile < total) issue_a();
+                    }
                 }
                 clk.lap(c_work);
                 if (dbg_on && leader) { atomicAdd(p.dbg + 0, c_wa); atomicAdd(p.dbg + 1, c_wb); atomicAdd(p.dbg + 2, c_work); }
@@ -626,6 +645,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const uint32_t b16 = b_plane16;                        // weight slot = [plane][tap][rows]: taps one plane tile apart
                 const uint32_t bp16 = (uint32_t)gb * b_plane16;
                 int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+                const bool resident = p.b_resident != 0;
+                if (resident && item0 < total) { mbar_wait(fullB0, 0); tc_fence_after(); }
                 for (int tile = item0; tile < total; tile += item_step) {
                     const TcPhaseGrid g = p.grid[decode(tile).phase];
                     // A offset (in 16-byte units) of tap (iy, ix) inside the patch: off0 + iy*sy + ix*sx
@@ -649,6 +670,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         const int te = centre_only ? 1 : g.ntaps;
                         uint32_t a_lo = a_lo0 + (centre_only ? (uint32_t)((hy0 * pw + hx0) * 8) : off0);
                         int ix = 0;
+                        if (resident) {
+                            // weights stay put: slab cb's taps start at cb * gb tiles, addressed by their device tap index
+                            const uint32_t b_lo = desc_lo(smem_u32(smem_b) + (uint32_t)(cb * gb * b_bytes)) + (uint32_t)(centre_only ? ctap : g.wi0) * b16;
+                            if (exp_mma & 128) {}
+                            else if (split) halo_taps_nk<PAIR, true>(nk, te, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, g.nx, ix, accumulate);
+                            else halo_taps_nk<PAIR, false>(nk, te, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, g.nx, ix, accumulate);
+                        } else
                         for (int t0 = 0; t0 < te; t0 += gb) {
                             const int ng = min(gb, te - t0);
                             clk.lap(c_work);

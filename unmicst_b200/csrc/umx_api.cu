@@ -551,6 +551,18 @@ int lower_conv_tc(umx_handle* h, Op& op) {
             while (tp.stages > 2 && budget < tp.stages * ab + 2 * (size_t)tp.gb * bb) tp.stages--;
             while (tp.gb > 1 && budget < tp.stages * ab + 2 * (size_t)tp.gb * bb) tp.gb--;
             tp.b_stages = budget > tp.stages * ab ? (int)std::min<size_t>(6, (budget - tp.stages * ab) / ((size_t)tp.gb * bb)) : 0;
+            // weight-stationary: when every weight tile of the layer (all taps of every slab, this CTA's share of the
+            // N rows) fits next to >= 3 patch slots, it is loaded once per CTA and the per-item weight traffic, barrier
+            // round trips and commits disappear (the 64x64 layers of the v2 graphs in single precision)
+            {
+                const int n_chunks = (tp.c0 + 63) / 64 + (tp.c1 + 63) / 64;
+                const size_t res = (size_t)n_chunks * ntaps_w * bb;
+                const char* e = getenv("UMX_TC_RESIDENT");
+                if ((e ? atoi(e) : 1) && tp.n_ntiles == 1 && ntaps_w <= 9 && budget >= res + 3 * ab) {
+                    tp.b_resident = 1; tp.gb = ntaps_w; tp.b_stages = n_chunks;
+                    tp.stages = (int)std::min<size_t>(6, (budget - res) / ab);
+                }
+            }
             if (tp.b_stages < 2) { tp.halo = 0; tp.bw = std::min(a0.w, 16); tp.bh = std::min(a0.h, 128 / tp.bw); tp.bn = 128 / (tp.bw * tp.bh); }
         }
         tp.kslab = 1;
@@ -566,7 +578,7 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     if (const char* e = getenv("UMX_TC_EXP")) tp.exp_flags = atoi(e);
     if (const char* e = getenv("UMX_TC_STAGES")) {
         const int cap = std::max(2, atoi(e));
-        if (tp.halo) tp.b_stages = std::min(tp.b_stages, cap); else tp.stages = std::min(tp.stages, cap);
+        if (tp.halo) { if (!tp.b_resident) tp.b_stages = std::min(tp.b_stages, cap); } else tp.stages = std::min(tp.stages, cap);
     }
     if (tp.stages < 2) { set_error("%s: pipeline does not fit shared memory", op.name.c_str()); return UMX_EINVAL; }
     tp.act = sp.act; tp.leaky = kLeaky; tp.pool = sp.pool ? 1 : 0;
@@ -792,8 +804,8 @@ int run_network(umx_handle* h, int nb, float* probs_out) {
                 UMX_CUDA_TRY(cudaMemcpyAsync(c, h->d_dbg, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
                 UMX_CUDA_TRY(cudaStreamSynchronize(h->stream));
                 const double n = c[15] ? (double)c[15] : 1.0;      // MMA-issuing CTAs
-                fprintf(stderr, "[umx dbg] %-14s tiles %5d halo %d pair %d stages %d/%d gb %d | producer waitA %.0f waitB %.0f work %.0f | mma waitT %.0f waitA %.0f waitB %.0f work %.0f | epi waitT %.0f work %.0f (kcycles per issuing CTA)\n",
-                        op.name.c_str(), nb, tp.halo, tp.pair, tp.stages, tp.b_stages, tp.gb, c[0] / n / 1e3, c[1] / n / 1e3, c[2] / n / 1e3,
+                fprintf(stderr, "[umx dbg] %-14s tiles %5d halo %d pair %d stages %d/%d gb %d res %d | producer waitA %.0f waitB %.0f work %.0f | mma waitT %.0f waitA %.0f waitB %.0f work %.0f | epi waitT %.0f work %.0f (kcycles per issuing CTA)\n",
+                        op.name.c_str(), nb, tp.halo, tp.pair, tp.stages, tp.b_stages, tp.gb, tp.b_resident, c[0] / n / 1e3, c[1] / n / 1e3, c[2] / n / 1e3,
                         c[4] / n / 1e3, c[5] / n / 1e3, c[6] / n / 1e3, c[7] / n / 1e3, c[8] / n / 1e3, c[9] / n / 1e3);
             }
         } else if (op.kind == OP_CONV && op.use_first) {

@@ -27,6 +27,7 @@ struct TcConvParams {
     int32_t halo;                // 1: one (bh+halo) x (bw+halo) pixel patch per 64-channel slab serves every tap
     int32_t pw, ph, hx0, hy0;    // patch size and left/top halo (halo mode)
     int32_t b_stages, gb;        // halo mode: weight ring depth, taps per weight slot
+    int32_t b_resident;          // halo mode: every (slab, tap) weight tile of the layer stays in shared memory (one slot of gb = all taps per slab)
     int32_t kslab;               // plain mode: 64-channel slabs per ring slot (more MMAs per barrier round trip)
     int32_t exp_flags;           // timing experiments only (results invalid): 1 no TMA loads, 4 one MMA per slab, 8 first epilogue chunk only, 16 no global stores, 32 no epilogue work
     unsigned long long* dbg;     // exp_flags & 64: 16 cycle counters (producer / MMA / epilogue waits and work), else nullptr
