@@ -285,7 +285,7 @@ __device__ __forceinline__ void halo_taps_nk(int nk, int ng, uint32_t tmem_d, ui
 
 // Everything the epilogue of one accumulator tile needs that does not change from item to item.
 struct EpiCtx {
-    const float* s_bias; const float* s_ps; const float* s_pt; const float* s_skipw; const float4* s_topw4;
+    const float* s_ps; const float* s_pt; const float* s_skipw; const float4* s_topw4;
     float* out_f; __half* out_h; int64_t out_plane_elems;
     int cout, out_cs, out_planes, act, pool, bw;
     float leaky;
@@ -296,12 +296,12 @@ struct EpiCtx {
 // Bias / shortcut / activation / post-affine of NC accumulator columns of one pixel, then either the fused lt logits
 // (TOPK > 0) or the 2x2 max-pool and the fp32 / fp16 hi[/lo] stores.  co = absolute output channel of column 0.
 template <int NC, int SKIPC, int TOPK>
-__device__ __forceinline__ void epi_chunk(const EpiCtx& e, const uint32_t (&r)[NC], int co, float xs, bool writer,
+__device__ __forceinline__ void epi_chunk(const TcConvParams& p, const EpiCtx& e, const uint32_t (&r)[NC], int co, float xs, bool writer,
                                           float* of, __half* oh, float (&z)[4]) {
     float v[NC];
 #pragma unroll
-    for (int j4 = 0; j4 < NC / 4; ++j4) {
-        const float4 b = *reinterpret_cast<const float4*>(e.s_bias + co + j4 * 4);
+    for (int j4 = 0; j4 < NC / 4; ++j4) {      // co is warp-uniform: constant-bank loads, no shared-memory traffic
+        const float4 b = *reinterpret_cast<const float4*>(p.tab_bias + co + j4 * 4);
         v[j4 * 4 + 0] = __uint_as_float(r[j4 * 4 + 0]) + b.x; v[j4 * 4 + 1] = __uint_as_float(r[j4 * 4 + 1]) + b.y;
         v[j4 * 4 + 2] = __uint_as_float(r[j4 * 4 + 2]) + b.z; v[j4 * 4 + 3] = __uint_as_float(r[j4 * 4 + 3]) + b.w;
     }
@@ -332,7 +332,7 @@ __device__ __forceinline__ void epi_chunk(const EpiCtx& e, const uint32_t (&r)[N
     if (TOPK > 0) {
 #pragma unroll
         for (int j = 0; j < NC; ++j) {
-            const float4 w = e.s_topw4[co + j];
+            const float4 w = e.s_topw4[co + j];       // one broadcast LDS.128 (the constant bank only offers 64-bit loads)
             z[0] = fmaf(v[j], w.x, z[0]); z[1] = fmaf(v[j], w.y, z[1]);
             if (TOPK > 2) z[2] = fmaf(v[j], w.z, z[2]);
             if (TOPK > 3) z[3] = fmaf(v[j], w.w, z[3]);
@@ -436,25 +436,20 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     // needs no channel guards): bias [cpad], post scale / shift [cpad] each, shortcut weights [cpad],
     // lt weights [cpad] x float4, lt bias [4], partial lt logits [2 acc stages][128 pixels][4]
     const int cpad = p.n_ntiles * p.n_t;
-    float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
-    float* s_ps = s_bias + cpad;
+    float* s_ps = reinterpret_cast<float*>(tmem_slot + 4);
     float* s_pt = s_ps + (p.post_scale ? cpad : 0);
     float* s_skipw = s_pt + (p.post_scale ? cpad : 0);
     float* s_topw = s_skipw + (SKIPC > 0 ? cpad : 0);
-    float* s_topb = s_topw + (TOPK > 0 ? 4 * cpad : 0);
-    float* s_z = s_topb + 4;
+    float* s_z = s_topw + (TOPK > 0 ? 4 * cpad : 0);
     for (int i = threadIdx.x; i < cpad; i += kThreads) {
-        s_bias[i] = (p.bias && i < p.cout) ? p.bias[i] : 0.f;
         if (p.post_scale) { s_ps[i] = i < p.cout ? p.post_scale[i] : 1.f; s_pt[i] = i < p.cout ? p.post_shift[i] : 0.f; }
         if (SKIPC > 0) s_skipw[i] = i < p.cout ? p.skip_w[i] : 0.f;
     }
-    if (TOPK > 0) {
-        for (int i = threadIdx.x; i < cpad * 4; i += kThreads)
-            s_topw[i] = ((i >> 2) < p.cout && (i & 3) < TOPK) ? p.top_w[(i >> 2) * TOPK + (i & 3)] : 0.f;
-        if (threadIdx.x < 4) s_topb[threadIdx.x] = (p.top_b && (int)threadIdx.x < TOPK) ? p.top_b[threadIdx.x] : 0.f;
-    }
+    if (TOPK > 0)
+        for (int i = threadIdx.x; i < cpad * 4; i += kThreads) s_topw[i] = p.tab_topw[i];
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: the compiler then knows it (and every table index derived from it) is warp-uniform
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int rank = PAIR ? (int)cluster_ctarank() : 0;
     const bool leader = rank == 0;
     if (warp == 0 && lane == 0) {
@@ -740,7 +735,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int q = warp & 3;                                     // TMEM lane quarter this warp may read
         const int sub = (warp - 2) >> 2;                            // which share of the N columns it handles
         EpiCtx e;
-        e.s_bias = s_bias; e.s_ps = s_ps; e.s_pt = s_pt; e.s_skipw = s_skipw; e.s_topw4 = reinterpret_cast<const float4*>(s_topw);
+        e.s_ps = s_ps; e.s_pt = s_pt; e.s_skipw = s_skipw; e.s_topw4 = reinterpret_cast<const float4*>(s_topw);
         e.out_f = p.out_f; e.out_h = p.out_h; e.out_plane_elems = p.out_plane_elems;
         e.cout = p.cout; e.out_cs = p.out_cs; e.out_planes = p.out_planes; e.act = p.act; e.pool = p.pool; e.bw = p.bw;
         e.leaky = p.leaky; e.has_post = p.post_scale != nullptr;
@@ -793,25 +788,25 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             if (lead8) {
                 tmem_ld_wait();
                 if (n_full > 0) tmem_ld16_issue(tb16, ra);
-                epi_chunk<8, SKIPC, TOPK>(e, rt, co0, xs, writer, of, oh, z);
+                epi_chunk<8, SKIPC, TOPK>(p, e, rt, co0, xs, writer, of, oh, z);
                 __syncwarp();        // reconverge before the next .sync.aligned TMEM instruction
                 if (n_full == 0 && tail8) tmem_ld8_issue(tb16, rt);
             }
             for (int i = 0; i < n_full; i += 2) {
                 tmem_ld_wait();
                 if (i + 1 < n_full) tmem_ld16_issue(tb16 + (i + 1) * 16, rb); else if (tail8) tmem_ld8_issue(tb16 + n_full * 16, rt);
-                epi_chunk<16, SKIPC, TOPK>(e, ra, cb16 + i * 16, xs, writer, of16 + i * 16, oh16 + i * 16, z);
+                epi_chunk<16, SKIPC, TOPK>(p, e, ra, cb16 + i * 16, xs, writer, of16 + i * 16, oh16 + i * 16, z);
                 __syncwarp();
                 if (i + 1 < n_full) {
                     tmem_ld_wait();
                     if (i + 2 < n_full) tmem_ld16_issue(tb16 + (i + 2) * 16, ra); else if (tail8) tmem_ld8_issue(tb16 + n_full * 16, rt);
-                    epi_chunk<16, SKIPC, TOPK>(e, rb, cb16 + (i + 1) * 16, xs, writer, of16 + (i + 1) * 16, oh16 + (i + 1) * 16, z);
+                    epi_chunk<16, SKIPC, TOPK>(p, e, rb, cb16 + (i + 1) * 16, xs, writer, of16 + (i + 1) * 16, oh16 + (i + 1) * 16, z);
                     __syncwarp();
                 }
             }
             if (tail8) {
                 tmem_ld_wait();
-                epi_chunk<8, SKIPC, TOPK>(e, rt, cb16 + n_full * 16, xs, writer, of16 + n_full * 16, oh16 + n_full * 16, z);
+                epi_chunk<8, SKIPC, TOPK>(p, e, rt, cb16 + n_full * 16, xs, writer, of16 + n_full * 16, oh16 + n_full * 16, z);
                 __syncwarp();
             }
             if (TOPK > 0) {
@@ -827,7 +822,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     }
                     float mx = -INFINITY, sum = 0.f;
 #pragma unroll
-                    for (int k = 0; k < TOPK; ++k) { z[k] += s_topb[k]; mx = fmaxf(mx, z[k]); }
+                    for (int k = 0; k < TOPK; ++k) { z[k] += p.tab_topb[k]; mx = fmaxf(mx, z[k]); }
 #pragma unroll
                     for (int k = 0; k < TOPK; ++k) { z[k] = expf(z[k] - mx); sum += z[k]; }
                     const float inv = 1.f / sum;
@@ -874,7 +869,7 @@ EncodeTiledFn encode_fn() {
 
 size_t tc_conv_fixed_bytes(const TcConvParams& p) {
     const size_t cpad = (size_t)p.n_ntiles * p.n_t;
-    const size_t tables = (cpad * ((p.post_scale ? 3 : 1) + (p.skip_src ? 1 : 0) + (p.top_w ? 4 : 0)) + 4 + (p.top_w ? 2 * (kEpiSub - 1) * 128 * 4 : 0) + 8) * sizeof(float);
+    const size_t tables = (cpad * ((p.post_scale ? 2 : 0) + (p.skip_src ? 1 : 0) + (p.top_w ? 4 : 0)) + (p.top_w ? 2 * (kEpiSub - 1) * 128 * 4 : 0) + 8) * sizeof(float);
     return (2 * (size_t)(p.stages + (p.halo ? p.b_stages : 0)) + 4) * 8 + 16 + tables + 1024;
 }
 size_t tc_conv_a_bytes(const TcConvParams& p) {

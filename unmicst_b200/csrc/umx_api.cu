@@ -533,7 +533,7 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     }
     {
         const size_t cpad = (size_t)tp.n_ntiles * tp.n_t;
-        const size_t tables = (cpad * ((sp.has_post ? 3 : 1) + (narrow ? 1 : 0) + (op.fuse_top >= 0 ? 4 : 0)) + 4 +
+        const size_t tables = (cpad * ((sp.has_post ? 2 : 0) + (narrow ? 1 : 0) + (op.fuse_top >= 0 ? 4 : 0)) +
                                (op.fuse_top >= 0 ? 2 * 3 * 128 * 4 : 0) + 8) * 4 + 64;
         const size_t budget = 227 * 1024 - 2048 - 512 - tables;
         const size_t bb = tc_conv_b_bytes(tp);
@@ -583,7 +583,8 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     if (tp.stages < 2) { set_error("%s: pipeline does not fit shared memory", op.name.c_str()); return UMX_EINVAL; }
     tp.act = sp.act; tp.leaky = kLeaky; tp.pool = sp.pool ? 1 : 0;
     float* d = nullptr;
-    if (sp.has_bias) { UMX_TRY(upload(h, sp.bias, &d)); tp.bias = d; }
+    if (tp.n_ntiles * tp.n_t > kTcMaxCols) { set_error("%s: %d output channels exceed the tensor path's tables", op.name.c_str(), sp.cout); return UMX_EINVAL; }
+    if (sp.has_bias) for (int i = 0; i < sp.cout; ++i) tp.tab_bias[i] = sp.bias[i];
     if (sp.has_post) {
         UMX_TRY(upload(h, sp.post_scale, &d)); tp.post_scale = d;
         UMX_TRY(upload(h, sp.post_shift, &d)); tp.post_shift = d;
@@ -616,9 +617,12 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     }
     if (op.fuse_top >= 0) {
         Op& top = h->ops[op.fuse_top];
-        UMX_TRY(upload(h, top.top_w, &d)); tp.top_w = d;
-        if (!top.top_b.empty()) { UMX_TRY(upload(h, top.top_b, &d)); tp.top_b = d; }
+        UMX_TRY(upload(h, top.top_w, &d)); tp.top_w = d;          // (pointer only marks the fusion; the kernel reads the tables below)
         tp.top_k = h->K;
+        if (sp.cout > 256) { set_error("%s: fused lt needs <= 256 channels", op.name.c_str()); return UMX_EINVAL; }
+        for (int c = 0; c < sp.cout; ++c)
+            for (int k = 0; k < h->K; ++k) tp.tab_topw[c * 4 + k] = top.top_w[(size_t)c * h->K + k];
+        for (int k = 0; k < h->K && k < (int)top.top_b.size(); ++k) tp.tab_topb[k] = top.top_b[k];
     }
     // Device tap order = phase by phase (the taps of a phase are contiguous, so halo mode fetches a whole group of
     // taps with one TMA box), followed by `gb` all-zero taps so a box that starts at the last tap never leaves the tensor.

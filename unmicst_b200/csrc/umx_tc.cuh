@@ -10,6 +10,8 @@ namespace umx {
 // The taps of one output phase form an ny x nx grid with constant steps, so the kernels walk them with adds instead
 // of table look-ups: tap (iy, ix) reads the input at (dy0 + dstep*iy, dx0 + dstep*ix) and the weight tap
 // wi0 + iy*wiy + ix*wix.  conv k x k: one phase, dstep +1; stride-2 conv-transpose: four sub-pixel phases, dstep -1.
+constexpr int kTcMaxCols = 1280;     // widest layer the tensor path takes (columns = n_ntiles * n_t)
+
 struct TcPhaseGrid { int32_t ntaps, nx, dy0, dx0, dstep, wi0, wiy, wix; };
 
 struct TcConvParams {
@@ -37,7 +39,6 @@ struct TcConvParams {
     int32_t pool;                // fused 2x2 max-pool (conv only)
     int32_t a1_center;           // 1: the second source is a 1x1 shortcut: its slabs join the K loop at the centre tap only
     int32_t center_tap;          // linear index (= device weight tap) of the (0,0) tap of a k x k conv
-    const float* bias;           // [cout] or nullptr
     const float* post_scale;     // [cout] affine applied after the activation (legacy: batch-norm follows the ReLU) or nullptr
     const float* post_shift;
     __half* out_h;               // fp16 plane(s) [planes][n][oh][ow][cout] or nullptr
@@ -50,10 +51,14 @@ struct TcConvParams {
     const float* skip_w;         // [cout] fp32
     int32_t skip_c;              // 1 when skip_src is set
     // fused lt 1x1 conv + softmax (replaces the activation store when top_w != nullptr)
-    const float* top_w;          // [cout][K]
-    const float* top_b;          // [K] or nullptr
+    const float* top_w;          // non-null marks the fusion (values live in tab_topw / tab_topb)
     float* top_probs;            // [n][oh][ow][K]
     int32_t top_k;
+    // Epilogue tables in the kernel-parameter constant bank (padded with zeros to n_ntiles * n_t entries): warp-uniform
+    // operands come from the constant cache instead of shared memory, whose bandwidth belongs to the tensor core
+    alignas(16) float tab_bias[kTcMaxCols];  // bias (0 when the layer has none)
+    alignas(16) float tab_topw[256 * 4];     // fused lt weights [channel][4]
+    float tab_topb[4];
 };
 
 size_t tc_conv_smem_bytes(const TcConvParams& p);
