@@ -67,6 +67,55 @@ def test_forward_v2_synthetic_weights(name, n):
     _check_probs(got, _oracle_fw(m)(tiles))
 
 
+@pytest.mark.parametrize("precision", ["fp32", "single", "auto"])
+@pytest.mark.parametrize("name,n", [("nucleiDAPI1-5", 9), ("nucleiDAPILAMIN", 3), ("CytoplasmIncell2", 2)])
+def test_forward_v2_every_precision(name, n, precision):
+    """The bench runs `auto` (-> fp16 operands, one MMA per product, when calibration allows); the library default is
+    the hi/lo split; `fp32` is the CUDA-core path.  All three must meet the same tolerance against the oracle."""
+    m = modelzoo.synthetic_model(name, seed=0)
+    rng = np.random.default_rng(17)
+    S, C = m.hp["imSize"], m.hp["nChannels"]
+    tiles = rng.normal(size=(n, S, S, C)).astype(np.float32)
+    with _engine(m, precision=precision) as e:
+        got = e.forward_tiles(tiles)
+        if precision == "auto":
+            assert e.auto_report["chosen"] in ("single", "split3")
+    _check_probs(got, _oracle_fw(m)(tiles))
+    if precision == "fp32":
+        assert np.abs(got - _oracle_fw(m)(tiles)).max() <= 2e-5
+
+
+@pytest.mark.parametrize("precision", ["split3", "single"])
+def test_forward_v2_many_tiles_odd_count(precision):
+    """Every persistent CTA loops over several work items, rings wrap, the last 4x4-grid box is partly empty."""
+    m = modelzoo.synthetic_model("nucleiDAPI1-5", seed=3)
+    rng = np.random.default_rng(19)
+    tiles = rng.normal(size=(77, 64, 64, 1)).astype(np.float32)
+    with _engine(m, precision=precision) as e:
+        got = e.forward_tiles(tiles)
+        again = e.forward_tiles(tiles[::-1].copy())[::-1]
+    _check_probs(got, _oracle_fw(m)(tiles))
+    assert np.array_equal(got, again)            # tiles are independent: batch composition does not change a bit
+
+
+def test_legacy_auto_falls_back_to_split(nuclei_model):
+    """Real legacy weights are too steep for one MMA per product: calibration must keep the hi/lo split."""
+    with _engine(nuclei_model, precision="auto") as e:
+        assert e.auto_report["chosen"] == "split3"
+        assert e.auto_report["single_vs_split3_max_abs_dp"] > e.auto_report["tolerance"]
+
+
+def test_image_single_precision_v2():
+    m = modelzoo.synthetic_model("nucleiDAPI1-5", seed=0)
+    rng = np.random.default_rng(23)
+    img = rng.random((150, 333))
+    with _engine(m, precision="single") as e:
+        u8, f32 = e.infer_image(img, want_f32=True)
+    want = pi2d_oracle.infer_image(img, _oracle_fw(m), 64, 1, m.mean, m.std, 32, accum_dtype=np.float64)
+    assert np.abs(f32 - want).max() <= TOL_P
+    assert np.abs(u8.astype(int) - np.uint8(255 * want).astype(int)).max() <= 1
+
+
 def test_forward_v2_steep_softmax():
     """Stress variant: logits scaled until the softmax is as steep as the real models'."""
     m = modelzoo.synthetic_model("nucleiDAPI1-5", seed=1, logit_gain=12.0)
