@@ -17,6 +17,8 @@
 // CTAs, two TMEM accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
 #include <stdio.h>
 
+#include <utility>
+
 #include "umx_kernels.cuh"
 #include "umx_tc.cuh"
 
@@ -412,7 +414,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     // Halo mode (high-resolution layers): ring A holds one (bh+halo) x (bw+halo) pixel patch per slab that serves
     // every tap (A is fetched from L2 once instead of once per tap); ring B holds the weights of `gb` taps per slot.
     const int planes = p.planes;
-    const int a_box_bytes = HALO ? p.ph * p.pw * 128 : kAPlaneBytes;           // bytes one TMA box delivers per plane
+    const int a_box_bytes = HALO ? p.bn * p.ph * p.pw * 128 : kAPlaneBytes;    // bytes one TMA box delivers per plane
     const int a_plane_bytes = HALO ? ((a_box_bytes + 1023) & ~1023) : kAPlaneBytes;
     const int a_bytes = planes * a_plane_bytes;
     const int b_plane_bytes = (PAIR ? p.n_t / 2 : p.n_t) * 128;     // pair mode: each CTA stages half of the N rows
@@ -497,6 +499,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const bool noload = (p.exp_flags & 1) != 0;          // timing experiment: barriers complete without any TMA traffic
             if constexpr (HALO) {
                 const int hx0 = p.hx0, hy0 = p.hy0, n_chunks = nch0 + nch1;
+                const bool nh = p.halo_nh != 0;
                 const uint32_t txA = (PAIR ? 2u : 1u) * (uint32_t)(planes * a_box_bytes);
                 int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
                 unsigned long long c_wa = 0, c_wb = 0, c_work = 0; DbgClock clk; clk.start(dbg_on);
@@ -516,9 +519,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     const uint32_t da = smem_u32(smem) + (uint32_t)(sa * stage_bytes);
                     if (noload) { if (leader) mbar_arrive(fa); }
                     else if (leader) mbar_expect_tx(fa, txA);
+                    const int c2 = nh ? ta.n0 : ta.y0 - hy0, c3 = nh ? ta.y0 - hy0 : ta.n0;     // {C, W, tiles, H} order on 8x8 grids
                     for (int pl = 0; pl < planes && !noload; ++pl) {
-                        if (PAIR) tma_load_5d_pair(da + pl * a_plane_bytes, mapA, fa, cc, ta.x0 - hx0, ta.y0 - hy0, ta.n0, pl);
-                        else tma_load_5d(da + pl * a_plane_bytes, mapA, fa, cc, ta.x0 - hx0, ta.y0 - hy0, ta.n0, pl);
+                        if (PAIR) tma_load_5d_pair(da + pl * a_plane_bytes, mapA, fa, cc, ta.x0 - hx0, c2, c3, pl);
+                        else tma_load_5d(da + pl * a_plane_bytes, mapA, fa, cc, ta.x0 - hx0, c2, c3, pl);
                     }
                     if (++sa == n_stages) { sa = 0; pa ^= 1; }
                     if (++a_cb == n_chunks) { a_cb = 0; a_tile += item_step; if (a_tile < total) ta = decode(a_tile); }
@@ -636,6 +640,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             unsigned long long c_wt = 0, c_wa = 0, c_wb = 0, c_work = 0; DbgClock clk; clk.start(dbg_on);
             if constexpr (HALO) {
                 const int pw = p.pw, hx0 = p.hx0, hy0 = p.hy0, n_chunks = nch0 + nch1;
+                const int prow = p.halo_nh ? pw * p.bn : pw;           // pixels between two image rows inside the patch
                 const uint32_t a_hi = desc_hi((uint32_t)pw * 128u);     // consecutive 8-pixel rows are one patch row apart
                 const uint32_t b16 = b_plane16;                        // weight slot = [plane][tap][rows]: taps one plane tile apart
                 const uint32_t bp16 = (uint32_t)gb * b_plane16;
@@ -645,8 +650,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 for (int tile = item0; tile < total; tile += item_step) {
                     const TcPhaseGrid g = p.grid[decode(tile).phase];
                     // A offset (in 16-byte units) of tap (iy, ix) inside the patch: off0 + iy*sy + ix*sx
-                    const int sx = g.dstep * 8, sy = g.dstep * pw * 8, row_back = sy - g.nx * sx;
-                    const uint32_t off0 = (uint32_t)(((g.dy0 + hy0) * pw + g.dx0 + hx0) * 8);
+                    const int sx = g.dstep * 8, sy = g.dstep * prow * 8, row_back = sy - g.nx * sx;
+                    const uint32_t off0 = (uint32_t)(((g.dy0 + hy0) * prow + g.dx0 + hx0) * 8);
                     clk.lap(c_work);
                     mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
                     clk.lap(c_wt);
@@ -663,7 +668,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         const uint32_t a_lo0 = desc_lo(smem_u32(smem) + (uint32_t)(sa * stage_bytes));
                         const bool centre_only = second && a1c;
                         const int te = centre_only ? 1 : g.ntaps;
-                        uint32_t a_lo = a_lo0 + (centre_only ? (uint32_t)((hy0 * pw + hx0) * 8) : off0);
+                        uint32_t a_lo = a_lo0 + (centre_only ? (uint32_t)((hy0 * prow + hx0) * 8) : off0);
                         int ix = 0;
                         if (resident) {
                             // weights stay put: slab cb's taps start at cb * gb tiles, addressed by their device tap index
@@ -737,7 +742,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         EpiCtx e;
         e.s_ps = s_ps; e.s_pt = s_pt; e.s_skipw = s_skipw; e.s_topw4 = reinterpret_cast<const float4*>(s_topw);
         e.out_f = p.out_f; e.out_h = p.out_h; e.out_plane_elems = p.out_plane_elems;
-        e.cout = p.cout; e.out_cs = p.out_cs; e.out_planes = p.out_planes; e.act = p.act; e.pool = p.pool; e.bw = p.bw;
+        e.cout = p.cout; e.out_cs = p.out_cs; e.out_planes = p.out_planes; e.act = p.act; e.pool = p.pool; e.bw = p.halo_nh ? p.bw * p.bn : p.bw;      // lane distance of the pixel one image row down
         e.leaky = p.leaky; e.has_post = p.post_scale != nullptr;
         e.wide_store = p.out_f == nullptr && p.out_h != nullptr && (p.out_cs & 15) == 0 && p.n_ntiles * p.n_t <= p.out_cs &&
                        (p.out_plane_elems & 15) == 0 && !(p.exp_flags & 512);
@@ -754,7 +759,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const bool nostore = (p.exp_flags & 16) != 0;
         const int in_h = p.in_h, in_w = p.in_w, os = p.os, n_tiles = p.n_tiles;
         const int m = q * 32 + lane;
-        const int xl = m % p.bw, yl = (m / p.bw) % p.bh, nl = m / (p.bw * p.bh);
+        const int xl = m % p.bw;
+        const int yl = p.halo_nh ? m / (p.bw * p.bn) : (m / p.bw) % p.bh, nl = p.halo_nh ? (m / p.bw) % p.bn : m / (p.bw * p.bh);
         const int oh_ = e.pool ? in_h >> 1 : in_h * os, ow_ = e.pool ? in_w >> 1 : in_w * os;
         int acc = 0; uint32_t acc_phase = 0;
         unsigned long long c_wt = 0, c_work = 0; DbgClock clk; clk.start(dbg_on && leader && lane == 0 && warp == 2);
@@ -873,7 +879,7 @@ size_t tc_conv_fixed_bytes(const TcConvParams& p) {
     return (2 * (size_t)(p.stages + (p.halo ? p.b_stages : 0)) + 4) * 8 + 16 + tables + 1024;
 }
 size_t tc_conv_a_bytes(const TcConvParams& p) {
-    const size_t box = p.halo ? (((size_t)p.ph * p.pw * 128 + 1023) & ~(size_t)1023) : (size_t)kAPlaneBytes;
+    const size_t box = p.halo ? (((size_t)p.bn * p.ph * p.pw * 128 + 1023) & ~(size_t)1023) : (size_t)kAPlaneBytes;
     return (size_t)p.planes * box;
 }
 size_t tc_conv_b_bytes(const TcConvParams& p) { return (size_t)p.planes * (size_t)(p.pair ? p.n_t / 2 : p.n_t) * 128; }
@@ -947,12 +953,15 @@ cudaError_t launch_tc_conv(const CUtensorMap& a0, const CUtensorMap& a1, const C
 }
 
 int make_act_tensor_map(CUtensorMap* out, const __half* base, int planes, int64_t plane_elems, int n, int h, int w, int c,
-                        int bw, int bh, int bn, int box_planes) {
+                        int bw, int bh, int bn, int box_planes, int nh_order) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return -1;
     cuuint64_t dims[5] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n, (cuuint64_t)planes};
     cuuint64_t strides[4] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2, (cuuint64_t)plane_elems * 2};
     cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn, (cuuint32_t)box_planes};
+    if (nh_order) {          // tiles before rows: box memory order [h][tile][w][c]
+        std::swap(dims[2], dims[3]); std::swap(strides[1], strides[2]); std::swap(box[2], box[3]);
+    }
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), dims, strides, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

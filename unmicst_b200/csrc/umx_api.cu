@@ -530,6 +530,17 @@ int lower_conv_tc(umx_handle* h, Op& op) {
             tp.hx0 = tt.hx0; tp.hy0 = tt.hy0;
             tp.pw = tp.bw + tt.hx0 + tt.hx1; tp.ph = tp.bh + tt.hy0 + tt.hy1;
         }
+        // 8x8 grids: two tiles per GEMM tile, patch rows interleaved [h][tile][w] (needs a tensor map whose tile
+        // dimension comes before the row dimension; probed here, plain mode if the driver refuses it)
+        const char* e8 = getenv("UMX_TC_HALO8");
+        if ((e ? atoi(e) : 1) && (e8 ? atoi(e8) : 1) && a0.w == 8 && a0.h == 8 && ntaps_w > 1 && !sp.transpose) {       // (conv-transpose measured slower: one patch per phase)
+            CUtensorMap probe;
+            const int pw = 8 + tt.hx0 + tt.hx1, ph = 8 + tt.hy0 + tt.hy1;
+            if (a0.dh && make_act_tensor_map(&probe, a0.dh, a0.planes, a0.plane_elems, h->cap_tiles, a0.h, a0.w, a0.cs(), pw, ph, 2, 1, 1) == 0) {
+                tp.halo = 1; tp.halo_nh = 1; tp.bw = 8; tp.bh = 8; tp.bn = 2;
+                tp.hx0 = tt.hx0; tp.hy0 = tt.hy0; tp.pw = pw; tp.ph = ph;
+            }
+        }
     }
     {
         const size_t cpad = (size_t)tp.n_ntiles * tp.n_t;
@@ -563,7 +574,7 @@ int lower_conv_tc(umx_handle* h, Op& op) {
                     tp.stages = (int)std::min<size_t>(6, (budget - res) / ab);
                 }
             }
-            if (tp.b_stages < 2) { tp.halo = 0; tp.bw = std::min(a0.w, 16); tp.bh = std::min(a0.h, 128 / tp.bw); tp.bn = 128 / (tp.bw * tp.bh); }
+            if (tp.b_stages < 2) { tp.halo = 0; tp.halo_nh = 0; tp.bw = std::min(a0.w, 16); tp.bh = std::min(a0.h, 128 / tp.bw); tp.bn = 128 / (tp.bw * tp.bh); }
         }
         tp.kslab = 1;
         if (!tp.halo) {
@@ -649,10 +660,10 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     if (rc) { set_error("%s: cuTensorMapEncodeTiled(weights) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
     if (!a0.dh || (a1 && !a1->dh)) { set_error("%s: fp16 source buffer missing", op.name.c_str()); return UMX_EINVAL; }
     const int box_w = tp.halo ? tp.pw : tp.bw, box_h = tp.halo ? tp.ph : tp.bh, box_p = tp.halo ? 1 : planes;
-    rc = make_act_tensor_map(&op.mapA0, a0.dh, a0.planes, a0.plane_elems, h->cap_tiles, a0.h, a0.w, a0.cs(), box_w, box_h, tp.bn, box_p);
+    rc = make_act_tensor_map(&op.mapA0, a0.dh, a0.planes, a0.plane_elems, h->cap_tiles, a0.h, a0.w, a0.cs(), box_w, box_h, tp.bn, box_p, tp.halo_nh);
     if (rc) { set_error("%s: cuTensorMapEncodeTiled(A0) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
     if (a1) {
-        rc = make_act_tensor_map(&op.mapA1, a1->dh, a1->planes, a1->plane_elems, h->cap_tiles, a1->h, a1->w, a1->cs(), box_w, box_h, tp.bn, box_p);
+        rc = make_act_tensor_map(&op.mapA1, a1->dh, a1->planes, a1->plane_elems, h->cap_tiles, a1->h, a1->w, a1->cs(), box_w, box_h, tp.bn, box_p, tp.halo_nh);
         if (rc) { set_error("%s: cuTensorMapEncodeTiled(A1) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
     } else {
         op.mapA1 = op.mapA0;

@@ -28,6 +28,8 @@ struct TcConvParams {
     int32_t stages;              // smem pipeline depth (halo mode: patch slots)
     int32_t halo;                // 1: one (bh+halo) x (bw+halo) pixel patch per 64-channel slab serves every tap
     int32_t pw, ph, hx0, hy0;    // patch size and left/top halo (halo mode)
+    int32_t halo_nh;             // halo mode on 8x8 grids: the patch holds bn tiles row-interleaved, [h][tile][w], so that
+                                 // consecutive 8-pixel row groups stay one patch row apart (uniform SBO); GEMM row m = (y*bn + tile)*bw + x
     int32_t b_stages, gb;        // halo mode: weight ring depth, taps per weight slot
     int32_t b_resident;          // halo mode: every (slab, tap) weight tile of the layer stays in shared memory (one slot of gb = all taps per slab)
     int32_t kslab;               // plain mode: 64-channel slabs per ring slot (more MMAs per barrier round trip)
@@ -71,8 +73,9 @@ cudaError_t launch_tc_conv(const CUtensorMap& a0, const CUtensorMap& a1, const C
 
 // Host helpers: build TMA descriptors through the driver entry point (no libcuda link dependency).
 // activations: fp16 [planes][n][h][w][c]; box = {64 ch, bw, bh, bn, planes}
+// nh_order: dimension order {C, W, tiles, H, plane} (box rows interleave the tiles) instead of {C, W, H, tiles, plane}
 int make_act_tensor_map(CUtensorMap* out, const __half* base, int planes, int64_t plane_elems, int n, int h, int w, int c,
-                        int bw, int bh, int bn, int box_planes);
+                        int bw, int bh, int bn, int box_planes, int nh_order = 0);
 // weights: fp16 [planes][tap][cout][cin]; box = {64 cin, n_t, box_taps, planes}
 int make_weight_tensor_map(CUtensorMap* out, const __half* base, int planes, int taps, int cout, int cin, int n_t,
                            int box_planes, int box_taps);
