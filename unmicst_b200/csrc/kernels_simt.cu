@@ -36,6 +36,27 @@ __device__ __forceinline__ void store_h2x4(__half* o, int64_t plane_elems, int p
     if (planes == 2) *reinterpret_cast<uint2*>(o + plane_elems) = *reinterpret_cast<uint2*>(l);
 }
 
+// 16 consecutive channels (32-byte aligned destination) -> one 256-bit store per plane
+__device__ __forceinline__ void store_h16(__half* o, int64_t plane_elems, int planes, const float* v) {
+    __half2 hi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hi[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    const uint32_t* h = reinterpret_cast<const uint32_t*>(hi);
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]),
+                 "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]) : "memory");
+    if (planes == 2) {
+        __half2 lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float2 f = __half22float2(hi[j]);
+            lo[j] = __floats2half2_rn(v[2 * j] - f.x, v[2 * j + 1] - f.y);
+        }
+        const uint32_t* l = reinterpret_cast<const uint32_t*>(lo);
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o + plane_elems), "r"(l[0]), "r"(l[1]), "r"(l[2]),
+                     "r"(l[3]), "r"(l[4]), "r"(l[5]), "r"(l[6]), "r"(l[7]) : "memory");
+    }
+}
+
 // Each CTA: 128 output pixels (nt image tiles x ph x pw) x 64 output channels of one phase.
 // Each thread: a 2x4 pixel patch x 4 output channels (32 fp32 accumulators).
 __global__ void __launch_bounds__(NTHR) conv_simt_kernel(const __grid_constant__ ConvParams p) {
@@ -263,15 +284,21 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const FirstParams p) {
             const int64_t pix = ((int64_t)n * p.S + y0 + 2 * py + (q >> 1)) * p.S + x0 + 2 * px + (q & 1);
             __half* o = p.taps_out + pix * p.taps_cs;
 #pragma unroll
-            for (int g = 0; g < (NCH + 7) / 8; ++g) {
-                float v[8];
+            const bool wide = (p.taps_cs & 15) == 0 && (p.taps_plane_elems & 15) == 0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int ch = g * 8 + j;
+            for (int g = 0; g < (NCH + 15) / 16; ++g) {
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int ch = g * 16 + j;
                     v[j] = ch < NCH ? in[(q >> 1) + (ch / CIN) / KS][(q & 1) + (ch / CIN) % KS][ch % CIN] : 0.f;
                 }
-                store_h2x4(o + g * 8, p.taps_plane_elems, p.taps_planes, v);
-                store_h2x4(o + g * 8 + 4, p.taps_plane_elems, p.taps_planes, v + 4);
+                if (wide) store_h16(o + g * 16, p.taps_plane_elems, p.taps_planes, v);
+                else {
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4)
+                        if (g * 16 + j4 * 4 < p.taps_cs) store_h2x4(o + g * 16 + j4 * 4, p.taps_plane_elems, p.taps_planes, v + j4 * 4);
+                }
             }
         }
     }
@@ -330,9 +357,13 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const FirstParams p) {
                 }
             }
             if (p.out_h) {
+                if ((p.out_cs & 15) == 0 && (p.out_plane_elems & 15) == 0 && cg + 16 <= p.out_cs)
+                    store_h16(p.out_h + opix * p.out_cs + cg, p.out_plane_elems, p.out_planes, v);
+                else {
 #pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4)
-                    if (cg + j4 * 4 < p.out_cs) store_h2x4(p.out_h + opix * p.out_cs + cg + j4 * 4, p.out_plane_elems, p.out_planes, v + j4 * 4);
+                    for (int j4 = 0; j4 < 4; ++j4)
+                        if (cg + j4 * 4 < p.out_cs) store_h2x4(p.out_h + opix * p.out_cs + cg + j4 * 4, p.out_plane_elems, p.out_planes, v + j4 * 4);
+                }
             }
         }
     }
