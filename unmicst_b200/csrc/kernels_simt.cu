@@ -454,9 +454,10 @@ __global__ void __launch_bounds__(256) gather_tiles_kernel(const GatherParams p)
     const int64_t total = (int64_t)p.n_tiles * p.S * p.S;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const int x = (int)(i % p.S);
-    const int y = (int)((i / p.S) % p.S);
-    const int tl = (int)(i / ((int64_t)p.S * p.S));
+    const int lg = 31 - __clz(p.S);               // imSize is a power of two (checked in umx_create)
+    const int x = (int)(i & (p.S - 1));
+    const int y = (int)((i >> lg) & (p.S - 1));
+    const int tl = (int)(i >> (2 * lg));
     const int t = p.tile0 + tl;
     const int ti = t / p.npc, tj = t % p.npc;
     const int r = ti * p.sub + y - p.margin;     // image row
