@@ -1,20 +1,22 @@
 // tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a.
 //
-// Computes tf.nn.conv2d (3x3, SAME, stride 1) and tf.nn.conv2d_transpose (3x3, stride 2, SAME, as
-// four sub-pixel phases) over NHWC activations of many independent PI2D tiles at once:
+// Computes tf.nn.conv2d (1x1 / 3x3 / 5x5, SAME, stride 1) and tf.nn.conv2d_transpose (stride 2, SAME, as four
+// sub-pixel phases) over NHWC activations of many independent PI2D tiles at once:
 //     GEMM M = 128 output pixels (a TMA box of bn tiles x bh rows x bw cols),
 //          N = n_t output channels (<= 256), K = taps x input channels in 64-channel slabs.
-// A (activations) is fetched per filter tap by a 5-D TMA tiled load whose box origin is shifted by
-// the tap offset; rows/cols outside an image tile are zero-filled by the TMA unit, which is exactly
-// TensorFlow's per-tile SAME padding.  The channel concat [skip, up] of the up path
-// (UnMicst1-5.py:196) is never materialised: the K loop walks two tensor maps.  B (weights, BN
-// folded) is K-major [tap][cout][cin].  Both land in 128B-swizzled shared memory and feed
-// tcgen05.mma (kind::f16, fp32 accumulate in TMEM).  Operands are fp16; in split mode every
-// activation/weight is carried as hi + lo fp16 planes and each product issues three MMAs
-// (hi*hi + hi*lo + lo*hi), which restores ~fp32 accuracy.
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocator), warps 2..5 = epilogue
-// (TMEM -> registers -> bias / leaky-ReLU / 2x2 max-pool -> fp16 hi/lo planes or fp32).  Persistent
-// CTAs, two TMEM accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
+// A (activations): plain mode fetches one box per (tap, slab) with the box origin shifted by the tap offset; halo
+// mode fetches one (bh+halo) x (bw+halo) pixel patch per slab and moves the UMMA descriptor inside it per tap.
+// Rows/cols outside an image tile are zero-filled by the TMA unit, which is exactly TensorFlow's per-tile SAME
+// padding.  The channel concat [skip, up] of the up path (UnMicst1-5.py:196) is never materialised: the K loop
+// walks two tensor maps.  B (weights, BN folded) is K-major [tap][cout][cin], streamed through a ring of slots of
+// `gb` taps or, when the whole layer fits, resident in shared memory.  Both operands land in 128B-swizzled shared
+// memory and feed tcgen05.mma (kind::f16, fp32 accumulate in TMEM).  Operands are fp16; in split mode every
+// activation/weight is carried as hi + lo fp16 planes and each product issues three MMAs (hi*hi + hi*lo + lo*hi),
+// which restores ~fp32 accuracy.
+// Warp roles: warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (+ TMEM allocator), warps 2..9 =
+// epilogue, two per TMEM lane quarter (TMEM -> registers -> bias / activation / 2x2 max-pool -> fp16 hi/lo planes
+// or fp32, or the fused lt 1x1 conv + softmax).  Persistent CTAs (optionally CTA pairs, cta_group::2), two TMEM
+// accumulator stages so the epilogue of item i overlaps the main loop of item i+1.
 #include <stdio.h>
 
 #include <utility>
