@@ -358,7 +358,8 @@ def run_ours(args):
             "metric": "megapixels/sec of K-class probability map", "value": value, "unit": "MP/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "split3": "f16 hi/lo split x3 MMA, f32 accumulate", "single": "f16, f32 accumulate"}[precision],
+            "dtype": {"fp32": "f32", "split3": "f16 hi/lo split x3 MMA, f32 accumulate", "single": "f16, f32 accumulate",
+                      "mixed": "f16 (per layer: 1 MMA or hi/lo split x3), f32 accumulate"}[precision],
             "data": "synthetic",
             "config": {"workload": cfg, "model": model_name,
                        "weights": "synthetic seed 0 (real checkpoint not shipped)" if model.synthetic else "real checkpoint (tests/golden/models)",

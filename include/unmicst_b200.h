@@ -49,6 +49,9 @@ extern "C" {
 #define UMX_PREC_FP32     1   /* every layer in fp32 FMA on the CUDA cores (exact reference arithmetic)     */
 #define UMX_PREC_SPLIT3   2   /* tcgen05 fp16 hi/lo split, 3 MMAs per product, fp32 accumulate (~fp32)      */
 #define UMX_PREC_SINGLE   3   /* tcgen05 fp16 operands, 1 MMA per product, fp32 accumulate                  */
+#define UMX_PREC_MIXED    4   /* per layer: umx_model_desc.reserved[0] (low) / [1] (high) is a bit mask over the   */
+                              /* ops in plan order (= entry order of umx_profile_read); set bits run with 1 MMA    */
+                              /* per product, the other tensor-path layers keep the hi/lo split                     */
 
 typedef struct umx_handle umx_handle;
 

@@ -79,7 +79,7 @@ def test_forward_v2_every_precision(name, n, precision):
     with _engine(m, precision=precision) as e:
         got = e.forward_tiles(tiles)
         if precision == "auto":
-            assert e.auto_report["chosen"] in ("single", "split3")
+            assert e.auto_report["chosen"] in ("single", "mixed", "split3")
     _check_probs(got, _oracle_fw(m)(tiles))
     if precision == "fp32":
         assert np.abs(got - _oracle_fw(m)(tiles)).max() <= 2e-5
@@ -98,11 +98,34 @@ def test_forward_v2_many_tiles_odd_count(precision):
     assert np.array_equal(got, again)            # tiles are independent: batch composition does not change a bit
 
 
-def test_legacy_auto_falls_back_to_split(nuclei_model):
-    """Real legacy weights are too steep for one MMA per product: calibration must keep the hi/lo split."""
+def test_legacy_auto_rejects_plain_single(sample_raw, nuclei_model):
+    """Real legacy weights are too steep for one MMA per product everywhere: calibration must not pick 'single', and
+    whatever it picks (per-layer 'mixed' or 'split3') must meet the contract against the oracle on real tiles."""
+    tiles = _real_tiles(sample_raw, nuclei_model, 12, seed=5)
     with _engine(nuclei_model, precision="auto") as e:
-        assert e.auto_report["chosen"] == "split3"
-        assert e.auto_report["single_vs_split3_max_abs_dp"] > e.auto_report["tolerance"]
+        rep = e.auto_report
+        got = e.forward_tiles(tiles)
+    assert rep["chosen"] in ("mixed", "split3")
+    assert rep["single_vs_split3_max_abs_dp"] > rep["tolerance"]
+    if rep["chosen"] == "mixed":
+        assert rep["single_layers"] and rep["mixed_vs_split3_max_abs_dp"] <= rep["tolerance"]
+    _check_probs(got, _oracle_fw(nuclei_model)(tiles))
+
+
+def test_mixed_precision_masks_v2():
+    """Any subset of layers may run with one MMA per product: all-zero mask == split3 bit for bit, a partial mask and
+    the full mask stay within the contract."""
+    m = modelzoo.synthetic_model("nucleiDAPI1-5", seed=0)
+    rng = np.random.default_rng(29)
+    tiles = rng.normal(size=(5, 64, 64, 1)).astype(np.float32)
+    want = _oracle_fw(m)(tiles)
+    with _engine(m, precision="split3") as e:
+        ref = e.forward_tiles(tiles)
+    with _engine(m, precision="mixed", single_mask=0) as e:
+        assert np.array_equal(e.forward_tiles(tiles), ref)
+    for mask in (0b0101010101010100, (1 << 40) - 1):
+        with _engine(m, precision="mixed", single_mask=mask) as e:
+            _check_probs(e.forward_tiles(tiles), want)
 
 
 def test_image_single_precision_v2():

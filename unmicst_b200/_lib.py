@@ -15,10 +15,11 @@ UMX_ABI_VERSION = 1
 UMX_OK, UMX_EINVAL, UMX_ENOTENSOR, UMX_ECUDA, UMX_ENOMEM, UMX_ENODEVICE = 0, -1, -2, -3, -4, -5
 UMX_GRAPH_LEGACY, UMX_GRAPH_V2 = 0, 1
 UMX_U8, UMX_U16, UMX_F32, UMX_F64 = 0, 1, 2, 3
-UMX_PREC_DEFAULT, UMX_PREC_FP32, UMX_PREC_SPLIT3, UMX_PREC_SINGLE = 0, 1, 2, 3
+UMX_PREC_DEFAULT, UMX_PREC_FP32, UMX_PREC_SPLIT3, UMX_PREC_SINGLE, UMX_PREC_MIXED = 0, 1, 2, 3, 4
 UMX_F_NO_SYNC = 1
 
-PRECISIONS = {"default": UMX_PREC_DEFAULT, "fp32": UMX_PREC_FP32, "split3": UMX_PREC_SPLIT3, "single": UMX_PREC_SINGLE}
+PRECISIONS = {"default": UMX_PREC_DEFAULT, "fp32": UMX_PREC_FP32, "split3": UMX_PREC_SPLIT3, "single": UMX_PREC_SINGLE,
+              "mixed": UMX_PREC_MIXED}
 
 
 class umx_model_desc(C.Structure):

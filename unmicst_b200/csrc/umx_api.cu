@@ -316,6 +316,16 @@ int build_plan(umx_handle* h) {
 
 enum { TC_NONE = 0, TC_PLAIN = 1, TC_SHORT_SKIP = 3, TC_SHORT_A1 = 4 };
 
+// fp16 operand planes of a tensor-path op: 1 = one MMA per product, 2 = hi/lo split (three MMAs)
+int op_planes(const umx_handle* h, const Op& op) {
+    if (h->precision == UMX_PREC_SINGLE) return 1;
+    if (h->precision == UMX_PREC_MIXED) {
+        const size_t idx = (size_t)(&op - h->ops.data());
+        return (idx < 64 && ((h->single_mask >> idx) & 1)) ? 1 : 2;
+    }
+    return 2;
+}
+
 // Which tensor-path form (if any) can run this op (after rewrite_narrow_sources).
 //  - one term: k x k conv / conv-transpose of one or two wide concat sources (TC_PLAIN); k = 1 is the tap-expanded
 //    first layer
@@ -489,7 +499,7 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     if (mode == TC_PLAIN && T.src1 >= 0) a1 = &h->bufs[T.src1];
     if (mode == TC_SHORT_A1) a1 = &h->bufs[sp.terms[1].src0];
     const Buffer* narrow = mode == TC_SHORT_SKIP ? &h->bufs[sp.terms[1].src0] : nullptr;
-    const int planes = h->precision == UMX_PREC_SINGLE ? 1 : 2;
+    const int planes = op_planes(h, op);
     tp.in_h = a0.h; tp.in_w = a0.w;
     tp.bw = std::min(a0.w, 16); tp.bh = std::min(a0.h, 128 / tp.bw); tp.bn = 128 / (tp.bw * tp.bh);
     tp.c0 = a0.cs(); tp.c1 = a1 ? a1->cs() : 0;          // storage channels (zero-padded to a multiple of 8)
@@ -701,7 +711,8 @@ int lower_plan(umx_handle* h) {
                 if (op.tc_mode == TC_SHORT_SKIP && ti == 1) { h->bufs[t.src0].need_f = true; continue; }
                 for (int s : {t.src0, t.src1}) {
                     if (s < 0) continue;
-                    if (op.use_tc) h->bufs[s].need_h = true; else h->bufs[s].need_f = true;
+                    if (op.use_tc) { h->bufs[s].need_h = true; if (op_planes(h, op) == 2) h->bufs[s].need_lo = true; }
+                    else h->bufs[s].need_f = true;
                 }
             }
         } else if (op.kind == OP_TAPS) {
@@ -712,10 +723,10 @@ int lower_plan(umx_handle* h) {
         }
     }
     h->bufs[h->in_buf].need_f = true;
-    const int planes = h->precision == UMX_PREC_SINGLE ? 1 : 2;
     for (auto& b : h->bufs) {
         if (b.need_f) UMX_CUDA_TRY(cudaMalloc(&b.d, (size_t)h->cap_tiles * b.per_tile() * sizeof(float)));
         if (b.need_h) {
+            const int planes = b.need_lo ? 2 : 1;         // the lo plane exists only where a split consumer reads it
             b.planes = planes; b.plane_elems = (int64_t)h->cap_tiles * b.per_tile_h();
             UMX_CUDA_TRY(cudaMalloc(&b.dh, (size_t)planes * b.plane_elems * sizeof(__half)));
             UMX_CUDA_TRY(cudaMemset(b.dh, 0, (size_t)planes * b.plane_elems * sizeof(__half)));
@@ -951,7 +962,8 @@ int umx_create(const umx_model_desc* desc, const umx_tensor* weights, int32_t n_
     // batch: enough tiles to fill 148 SMs several times over, bounded by workspace memory
     h->num_sms = prop.multiProcessorCount;
     h->precision = desc->precision == UMX_PREC_DEFAULT ? UMX_PREC_SPLIT3 : desc->precision;
-    if (h->precision < UMX_PREC_FP32 || h->precision > UMX_PREC_SINGLE) { set_error("unknown precision %d", desc->precision); umx_destroy(h); return UMX_EINVAL; }
+    if (h->precision == UMX_PREC_MIXED) h->single_mask = (uint64_t)(uint32_t)desc->reserved[0] | ((uint64_t)(uint32_t)desc->reserved[1] << 32);
+    if (h->precision < UMX_PREC_FP32 || h->precision > UMX_PREC_MIXED) { set_error("unknown precision %d", desc->precision); umx_destroy(h); return UMX_EINVAL; }
     rc = rewrite_narrow_sources(h);
     if (rc != UMX_OK) { umx_destroy(h); return rc; }
     int64_t per_tile = 0;

@@ -41,7 +41,7 @@ struct HostTensor {
 struct Buffer {
     std::string name;
     int h = 0, w = 0, c = 0;
-    bool need_f = false, need_h = false;
+    bool need_f = false, need_h = false, need_lo = false;     // need_lo: some consumer multiplies with the hi/lo split
     float* d = nullptr;             // [cap][h][w][c] fp32
     __half* dh = nullptr;           // [planes][cap][h][w][c] fp16
     int planes = 0;
@@ -117,6 +117,7 @@ struct umx_handle {
     int cap_tiles = 0;                           // workspace capacity in tiles (max_batch rounded up to 8)
     int num_sms = 148;
     int precision = UMX_PREC_SPLIT3;
+    uint64_t single_mask = 0;                    // UMX_PREC_MIXED: ops (by index) that run with one MMA per product
     std::vector<int> chan;                       // nOutX
     std::map<std::string, umx::HostTensor> tensors;
     std::vector<float*> dev_allocs;              // weights etc.

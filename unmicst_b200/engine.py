@@ -89,24 +89,56 @@ AUTO_TOLERANCE = 5e-4     # max|dp| of fp16 single-pass vs split3 on the probe t
 class Engine:
     """precision: 'default'/'split3' (fp16 hi/lo split, ~fp32 accurate, always within the 2e-3 contract),
     'single' (one fp16 MMA per product: ~3x less tensor work, accuracy depends on how steep the
-    model's softmax is), 'fp32' (CUDA cores only), or 'auto': build both tensor variants, run probe
-    tiles through them and keep 'single' only if it stays within AUTO_TOLERANCE of 'split3'."""
+    model's softmax is), 'mixed' (per layer: ``single_mask`` bit i = op i of ``profile_read`` runs single),
+    'fp32' (CUDA cores only), or 'auto': calibrate on probe tiles against 'split3' — keep 'single' if it
+    stays within AUTO_TOLERANCE, otherwise switch layers to single greedily (most expensive first) for as
+    long as the probe stays within the tolerance ('mixed'), which may end at plain 'split3'."""
 
     def __init__(self, model: Model, device: int = 0, precision: str = "default", max_batch_tiles: int = 0,
-                 probe_tiles: Optional[np.ndarray] = None):
+                 probe_tiles: Optional[np.ndarray] = None, single_mask: int = 0):
         self.auto_report = None
+        self.single_mask = 0
         if precision == "auto":
-            ref = Engine(model, device, "split3", max_batch_tiles)
-            cand = Engine(model, device, "single", max_batch_tiles)
+            probe_batch = 64
+            ref = Engine(model, device, "split3", probe_batch)
             if probe_tiles is None:
                 rng = np.random.default_rng(2024)
                 probe_tiles = rng.normal(size=(16, ref.S, ref.S, ref.C)).astype(np.float32)
-            d = float(np.abs(ref.forward_tiles(probe_tiles) - cand.forward_tiles(probe_tiles)).max())
-            keep, drop = (cand, ref) if d <= AUTO_TOLERANCE else (ref, cand)
-            drop.close()
-            self.__dict__.update(keep.__dict__)
-            keep._h = None
-            self.auto_report = {"single_vs_split3_max_abs_dp": d, "tolerance": AUTO_TOLERANCE, "chosen": self.precision}
+            want = ref.forward_tiles(probe_tiles)
+
+            def err_of(prec: str, mask: int = 0) -> float:
+                with Engine(model, device, prec, probe_batch, single_mask=mask) as e:
+                    return float(np.abs(e.forward_tiles(probe_tiles) - want).max())
+
+            d_single = err_of("single")
+            report = {"single_vs_split3_max_abs_dp": d_single, "tolerance": AUTO_TOLERANCE}
+            if d_single <= AUTO_TOLERANCE:
+                chosen, mask = "single", 0
+            else:
+                # cost per op from one profiled pass of the split engine; candidates = tensor-path layers
+                ref.profile_enable(True)
+                ref.forward_tiles(probe_tiles)
+                prof = ref.profile_read()
+                ref.profile_enable(False)
+                order = sorted((i for i, p in enumerate(prof) if p["flops"] > 0 and p["launches"] > 0 and i < 64),
+                               key=lambda i: -prof[i]["ms"])
+                mask, kept, d_mixed = 0, [], 0.0
+                for i in order:
+                    d = err_of("mixed", mask | (1 << i))
+                    if d == d_mixed:
+                        continue                              # the bit changes nothing: not a tensor-path layer
+                    if d <= AUTO_TOLERANCE:
+                        mask |= 1 << i
+                        kept.append(prof[i]["name"])
+                        d_mixed = d
+                chosen = "mixed" if mask else "split3"
+                report.update({"single_layers": kept, "mixed_vs_split3_max_abs_dp": d_mixed})
+            ref.close()
+            final = Engine(model, device, chosen, max_batch_tiles, single_mask=mask)
+            self.__dict__.update(final.__dict__)
+            final._h = None
+            report["chosen"] = chosen
+            self.auto_report = report
             return
         L = lib()
         hp = model.hp
@@ -123,6 +155,11 @@ class Engine:
         desc.ks, desc.n_extra_convs = int(hp["ks"]), int(hp["nExtraConvs"])
         desc.precision = _lib.PRECISIONS[precision]
         desc.max_batch_tiles = int(max_batch_tiles)
+        if precision == "mixed":
+            self.single_mask = int(single_mask) & (2 ** 64 - 1)
+            lo, hi = self.single_mask & 0xFFFFFFFF, self.single_mask >> 32
+            desc.reserved[0] = lo - (1 << 32) if lo >= 1 << 31 else lo        # bit pattern into the int32 fields
+            desc.reserved[1] = hi - (1 << 32) if hi >= 1 << 31 else hi
         names = sorted(model.weights)
         arr = (_lib.umx_tensor * len(names))()
         keep = []
