@@ -408,7 +408,8 @@ __device__ __forceinline__ void epi_chunk(const TcConvParams& p, const EpiCtx& e
 template <int SKIPC, int TOPK, bool PAIR, bool HALO>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-               const __grid_constant__ CUtensorMap mapB, const __grid_constant__ TcConvParams p) {
+               const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapB1,
+               const __grid_constant__ TcConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B swizzle; computed as an offset so the pointers stay provably shared-space
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -428,7 +429,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int nb_stages = HALO ? p.b_stages : 0;
     const int gb = HALO ? p.gb : 1;
     uint8_t* smem_b = smem + (size_t)n_stages * stage_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)nb_stages * gb * b_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (HALO && p.b_resident ? (size_t)p.b_res_bytes : (size_t)nb_stages * gb * b_bytes));
     const uint32_t full0 = smem_u32(bars);
     const uint32_t empty0 = full0 + 8 * n_stages;
     const uint32_t fullB0 = empty0 + 8 * n_stages;
@@ -460,6 +461,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tma_prefetch_desc(&mapA0);
         if (p.c1 > 0) tma_prefetch_desc(&mapA1);
         tma_prefetch_desc(&mapB);
+        if (p.b_resident && p.a1_center) tma_prefetch_desc(&mapB1);
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -564,14 +566,21 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     if (item0 < total) {
                         if (noload) { if (leader) mbar_arrive(fullB0); }
                         else {
-                            if (leader) mbar_expect_tx(fullB0, (uint32_t)n_chunks * txB);
+                            if (leader) mbar_expect_tx(fullB0, (PAIR ? 2u : 1u) * (uint32_t)p.b_res_bytes);
                             const int ncol = PAIR ? rank * (n_t / 2) : 0;
+                            uint32_t db = smem_u32(smem_b);
                             for (int cb = 0; cb < n_chunks; ++cb) {
                                 const bool second = cb >= nch0;
                                 const int kc = (second ? c0s : 0) + (second ? cb - nch0 : cb) * 64;
-                                const uint32_t db = smem_u32(smem_b) + (uint32_t)(cb * gb * b_bytes);
-                                if (PAIR) tma_load_4d_pair(db, &mapB, fullB0, kc, ncol, 0, 0);
-                                else tma_load_4d(db, &mapB, fullB0, kc, ncol, 0, 0);
+                                if (second && a1c) {        // 1x1 term: only its centre tap exists (one-tap box)
+                                    if (PAIR) tma_load_4d_pair(db, &mapB1, fullB0, kc, ncol, ctap, 0);
+                                    else tma_load_4d(db, &mapB1, fullB0, kc, ncol, ctap, 0);
+                                    db += b_bytes;
+                                } else {
+                                    if (PAIR) tma_load_4d_pair(db, &mapB, fullB0, kc, ncol, 0, 0);
+                                    else tma_load_4d(db, &mapB, fullB0, kc, ncol, 0, 0);
+                                    db += gb * b_bytes;
+                                }
                             }
                         }
                     }
@@ -674,7 +683,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         int ix = 0;
                         if (resident) {
                             // weights stay put: slab cb's taps start at cb * gb tiles, addressed by their device tap index
-                            const uint32_t b_lo = desc_lo(smem_u32(smem_b) + (uint32_t)(cb * gb * b_bytes)) + (uint32_t)(centre_only ? ctap : g.wi0) * b16;
+                            // (a centre-only slab keeps just that one tap, so the slabs after it start gb - 1 tiles earlier)
+                            const uint32_t r_off = (uint32_t)((second && a1c ? nch0 * gb + (cb - nch0) : cb * gb) * b_bytes);
+                            const uint32_t b_lo = desc_lo(smem_u32(smem_b) + r_off) + (centre_only ? 0u : (uint32_t)g.wi0 * b16);
                             if (exp_mma & 128) {}
                             else if (split) halo_taps_nk<PAIR, true>(nk, te, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, g.nx, ix, accumulate);
                             else halo_taps_nk<PAIR, false>(nk, te, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, g.nx, ix, accumulate);
@@ -886,7 +897,7 @@ size_t tc_conv_a_bytes(const TcConvParams& p) {
 }
 size_t tc_conv_b_bytes(const TcConvParams& p) { return (size_t)p.planes * (size_t)(p.pair ? p.n_t / 2 : p.n_t) * 128; }
 size_t tc_conv_smem_bytes(const TcConvParams& p) {
-    if (p.halo) return p.stages * tc_conv_a_bytes(p) + (size_t)p.b_stages * p.gb * tc_conv_b_bytes(p) + tc_conv_fixed_bytes(p);
+    if (p.halo) return p.stages * tc_conv_a_bytes(p) + (p.b_resident ? (size_t)p.b_res_bytes : (size_t)p.b_stages * p.gb * tc_conv_b_bytes(p)) + tc_conv_fixed_bytes(p);
     return p.stages * (size_t)(p.kslab > 0 ? p.kslab : 1) * (tc_conv_a_bytes(p) + tc_conv_b_bytes(p)) + tc_conv_fixed_bytes(p);
 }
 
@@ -914,7 +925,7 @@ cudaError_t tc_conv_configure() {
 }
 
 template <int SKIPC, int TOPK, bool PAIR, bool HALO>
-static cudaError_t launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcConvParams& p,
+static cudaError_t launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& b1, const TcConvParams& p,
                               int grid, size_t smem, cudaStream_t s) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -922,18 +933,18 @@ static cudaError_t launch_one(const CUtensorMap& a0, const CUtensorMap& a1, cons
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, tc_conv_kernel<SKIPC, TOPK, PAIR, HALO>, a0, a1, b, p);
+    return cudaLaunchKernelEx(&cfg, tc_conv_kernel<SKIPC, TOPK, PAIR, HALO>, a0, a1, b, b1, p);
 }
 
 template <int SKIPC, int TOPK>
-static cudaError_t launch_epi(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcConvParams& p,
+static cudaError_t launch_epi(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& b1, const TcConvParams& p,
                               int grid, size_t smem, cudaStream_t s) {
-    if (p.pair) return p.halo ? launch_one<SKIPC, TOPK, true, true>(a0, a1, b, p, grid, smem, s) : launch_one<SKIPC, TOPK, true, false>(a0, a1, b, p, grid, smem, s);
-    return p.halo ? launch_one<SKIPC, TOPK, false, true>(a0, a1, b, p, grid, smem, s) : launch_one<SKIPC, TOPK, false, false>(a0, a1, b, p, grid, smem, s);
+    if (p.pair) return p.halo ? launch_one<SKIPC, TOPK, true, true>(a0, a1, b, b1, p, grid, smem, s) : launch_one<SKIPC, TOPK, true, false>(a0, a1, b, b1, p, grid, smem, s);
+    return p.halo ? launch_one<SKIPC, TOPK, false, true>(a0, a1, b, b1, p, grid, smem, s) : launch_one<SKIPC, TOPK, false, false>(a0, a1, b, b1, p, grid, smem, s);
 }
 
-cudaError_t launch_tc_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const TcConvParams& p,
-                           int num_sms, cudaStream_t s) {
+cudaError_t launch_tc_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& b1,
+                           const TcConvParams& p, int num_sms, cudaStream_t s) {
     const int m_tiles = (p.bn > 1) ? (p.n_tiles + p.bn - 1) / p.bn : p.n_tiles * (p.in_w / p.bw) * (p.in_h / p.bh);
     const int per_unit = p.pair ? 2 : 1;
     const int total = p.nphase * ((m_tiles + per_unit - 1) / per_unit) * p.n_ntiles;
@@ -946,11 +957,11 @@ cudaError_t launch_tc_conv(const CUtensorMap& a0, const CUtensorMap& a1, const C
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     const bool skip = p.skip_src != nullptr;
     if (skip && (p.skip_c != 1 || p.top_w)) return cudaErrorInvalidValue;
-    if (skip) return launch_epi<1, 0>(a0, a1, b, p, grid, smem, s);
-    if (!p.top_w) return launch_epi<0, 0>(a0, a1, b, p, grid, smem, s);
-    if (p.top_k == 2) return launch_epi<0, 2>(a0, a1, b, p, grid, smem, s);
-    if (p.top_k == 3) return launch_epi<0, 3>(a0, a1, b, p, grid, smem, s);
-    if (p.top_k == 4) return launch_epi<0, 4>(a0, a1, b, p, grid, smem, s);
+    if (skip) return launch_epi<1, 0>(a0, a1, b, b1, p, grid, smem, s);
+    if (!p.top_w) return launch_epi<0, 0>(a0, a1, b, b1, p, grid, smem, s);
+    if (p.top_k == 2) return launch_epi<0, 2>(a0, a1, b, b1, p, grid, smem, s);
+    if (p.top_k == 3) return launch_epi<0, 3>(a0, a1, b, b1, p, grid, smem, s);
+    if (p.top_k == 4) return launch_epi<0, 4>(a0, a1, b, b1, p, grid, smem, s);
     return cudaErrorInvalidValue;
 }
 

@@ -576,11 +576,12 @@ int lower_conv_tc(umx_handle* h, Op& op) {
             // N rows) fits next to >= 3 patch slots, it is loaded once per CTA and the per-item weight traffic, barrier
             // round trips and commits disappear (the 64x64 layers of the v2 graphs in single precision)
             {
-                const int n_chunks = (tp.c0 + 63) / 64 + (tp.c1 + 63) / 64;
-                const size_t res = (size_t)n_chunks * ntaps_w * bb;
+                const int nc0 = (tp.c0 + 63) / 64, nc1 = (tp.c1 + 63) / 64, n_chunks = nc0 + nc1;
+                // (the slabs of a 1x1 term exist at the centre tap only: one tile each instead of ntaps_w)
+                const size_t res = ((size_t)nc0 * ntaps_w + (size_t)nc1 * (tp.a1_center ? 1 : ntaps_w)) * bb;
                 const char* e = getenv("UMX_TC_RESIDENT");
-                if ((e ? atoi(e) : 1) && tp.n_ntiles == 1 && ntaps_w <= 9 && budget >= res + 3 * ab) {
-                    tp.b_resident = 1; tp.gb = ntaps_w; tp.b_stages = n_chunks;
+                if ((e ? atoi(e) : 1) && tp.n_ntiles == 1 && ntaps_w <= 9 && planes == 1 && budget >= res + 3 * ab) {
+                    tp.b_resident = 1; tp.gb = ntaps_w; tp.b_stages = n_chunks; tp.b_res_bytes = (int32_t)res;
                     tp.stages = (int)std::min<size_t>(6, (budget - res) / ab);
                 }
             }
@@ -668,6 +669,11 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     UMX_CUDA_TRY(cudaMemcpy(dw, wh.data(), wh.size() * sizeof(__half), cudaMemcpyHostToDevice));
     int rc = make_weight_tensor_map(&op.mapB, dw, planes, taps_dev, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, planes, box_taps);
     if (rc) { set_error("%s: cuTensorMapEncodeTiled(weights) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
+    op.mapB1 = op.mapB;
+    if (tp.b_resident && tp.a1_center) {
+        rc = make_weight_tensor_map(&op.mapB1, dw, planes, taps_dev, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, planes, 1);
+        if (rc) { set_error("%s: cuTensorMapEncodeTiled(weights, one tap) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
+    }
     if (!a0.dh || (a1 && !a1->dh)) { set_error("%s: fp16 source buffer missing", op.name.c_str()); return UMX_EINVAL; }
     const int box_w = tp.halo ? tp.pw : tp.bw, box_h = tp.halo ? tp.ph : tp.bh, box_p = tp.halo ? 1 : planes;
     rc = make_act_tensor_map(&op.mapA0, a0.dh, a0.planes, a0.plane_elems, h->cap_tiles, a0.h, a0.w, a0.cs(), box_w, box_h, tp.bn, box_p, tp.halo_nh);
@@ -824,7 +830,7 @@ int run_network(umx_handle* h, int nb, float* probs_out) {
                 UMX_CUDA_TRY(cudaMemsetAsync(h->d_dbg, 0, 16 * sizeof(unsigned long long), h->stream));
                 tp.dbg = h->d_dbg;
             }
-            UMX_CUDA_TRY(launch_tc_conv(op.mapA0, op.mapA1, op.mapB, tp, h->num_sms, h->stream));
+            UMX_CUDA_TRY(launch_tc_conv(op.mapA0, op.mapA1, op.mapB, op.mapB1, tp, h->num_sms, h->stream));
             if (tp.exp_flags & 64) {
                 unsigned long long c[16];
                 UMX_CUDA_TRY(cudaMemcpyAsync(c, h->d_dbg, sizeof(c), cudaMemcpyDeviceToHost, h->stream));

@@ -82,7 +82,7 @@ struct Op {
     bool fused_away = false;         // OP_TOP executed inside the preceding conv
     ConvParams cp{};                 // fp32 CUDA-core implementation
     TcConvParams tcp{};              // tcgen05 implementation
-    alignas(64) CUtensorMap mapA0, mapA1, mapB;
+    alignas(64) CUtensorMap mapA0, mapA1, mapB, mapB1;
     TopParams tp{};
     TapsParams taps{};               // OP_TAPS: k x k tap expansion of a narrow buffer
     int taps_src = -1, taps_k = 0;

@@ -31,6 +31,7 @@ struct TcConvParams {
     int32_t halo_nh;             // halo mode on 8x8 grids: the patch holds bn tiles row-interleaved, [h][tile][w], so that
                                  // consecutive 8-pixel row groups stay one patch row apart (uniform SBO); GEMM row m = (y*bn + tile)*bw + x
     int32_t b_stages, gb;        // halo mode: weight ring depth, taps per weight slot
+    int32_t b_res_bytes;         // bytes of the resident weight region (per CTA)
     int32_t b_resident;          // halo mode: every (slab, tap) weight tile of the layer stays in shared memory (one slot of gb = all taps per slab)
     int32_t kslab;               // plain mode: 64-channel slabs per ring slot (more MMAs per barrier round trip)
     int32_t exp_flags;           // timing experiments only (results invalid): 1 no TMA loads, 4 one MMA per slab, 8 first epilogue chunk only, 16 no global stores, 32 no epilogue work
@@ -68,7 +69,8 @@ size_t tc_conv_a_bytes(const TcConvParams& p);
 size_t tc_conv_b_bytes(const TcConvParams& p);
 size_t tc_conv_fixed_bytes(const TcConvParams& p);
 cudaError_t tc_conv_configure();
-cudaError_t launch_tc_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+// b1: the weight map with a one-tap box (resident mode, centre-only slabs); equal to b when unused
+cudaError_t launch_tc_conv(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& b1,
                            const TcConvParams& p, int num_sms, cudaStream_t s);
 
 // Host helpers: build TMA descriptors through the driver entry point (no libcuda link dependency).
