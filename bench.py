@@ -344,8 +344,12 @@ def run_ours(args):
         if isinstance(ent, dict) and dom["launches"]:
             my_tiles = (band[1] - max(band[0] - 1, 0)) * npc if band else 0
             traffic = ent["dram_bytes_per_tile"] * my_tiles / dom["launches"]
+    # per-layer roofline of the whole step: sum over kernels of max(FLOPs / tensor peak, bytes / HBM peak)
+    # with the algorithmic FLOPs and 4-byte activation bytes the library accounts per launch
+    roof_ms = sum(max(p["flops"] / (peaks["tc_sustained"] * 1e12), p["bytes"] / (peaks["hbm"] * 1e9)) * 1e3 for p in prof)
     roofline = {"kernel": dom["name"], "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peaks["source"],
+                "step": {"per_layer_roofline_ms": roof_ms, "measured_ms": total_ms, "frac": roof_ms / total_ms if total_ms else None},
                 "avg_launch_ms": dom["ms"] / max(1, dom["launches"]), "share_of_step": dom["ms"] / total_ms,
                 "kernels": [{"name": p["name"], "ms": round(p["ms"], 3), "launches": p["launches"],
                              "tflops": round(p["flops"] / (p["ms"] * 1e-3) / 1e12, 2) if p["ms"] else 0,
