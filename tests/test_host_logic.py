@@ -129,3 +129,20 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(d, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_mixed_precision_mask_packing():
+    """UMX_PREC_MIXED carries its 64-bit op mask in two int32 fields: bit patterns must survive the signed ctypes fields
+    (the C side reassembles them as (uint32)lo | (uint64)(uint32)hi << 32, umx_api.cu umx_create)."""
+    import ctypes as C
+    from unmicst_b200.engine import mask_to_reserved
+    from unmicst_b200 import _lib
+    for mask in (0, 1, 0b1010, (1 << 31), (1 << 32) - 1, (1 << 32), (1 << 63) | 5, 2 ** 64 - 1, 2 ** 64 + 3):
+        lo, hi = mask_to_reserved(mask)
+        assert -(1 << 31) <= lo < (1 << 31) and -(1 << 31) <= hi < (1 << 31)
+        d = _lib.umx_model_desc()
+        d.reserved[0], d.reserved[1] = lo, hi
+        back = (d.reserved[0] & 0xFFFFFFFF) | ((d.reserved[1] & 0xFFFFFFFF) << 32)
+        assert back == mask & (2 ** 64 - 1)
+    assert _lib.PRECISIONS["mixed"] == 4
+    assert C.sizeof(_lib.umx_model_desc) == 16 * 4

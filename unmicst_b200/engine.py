@@ -86,6 +86,14 @@ def band_rows_py(H: int, S: int, tile_rows: Tuple[int, int]) -> Tuple[int, int]:
 AUTO_TOLERANCE = 5e-4     # max|dp| of fp16 single-pass vs split3 on the probe tiles (4x under the 2e-3 contract)
 
 
+def mask_to_reserved(mask: int) -> Tuple[int, int]:
+    """64-bit op mask of UMX_PREC_MIXED -> the two int32 fields umx_model_desc.reserved[0] (low word) and [1] (high
+    word) carry it in: same bit patterns, expressed as signed 32-bit values for ctypes."""
+    mask &= 2 ** 64 - 1
+    words = (mask & 0xFFFFFFFF, mask >> 32)
+    return tuple(w - (1 << 32) if w >= 1 << 31 else w for w in words)
+
+
 class Engine:
     """precision: 'default'/'split3' (fp16 hi/lo split, ~fp32 accurate, always within the 2e-3 contract),
     'single' (one fp16 MMA per product: ~3x less tensor work, accuracy depends on how steep the
@@ -157,9 +165,7 @@ class Engine:
         desc.max_batch_tiles = int(max_batch_tiles)
         if precision == "mixed":
             self.single_mask = int(single_mask) & (2 ** 64 - 1)
-            lo, hi = self.single_mask & 0xFFFFFFFF, self.single_mask >> 32
-            desc.reserved[0] = lo - (1 << 32) if lo >= 1 << 31 else lo        # bit pattern into the int32 fields
-            desc.reserved[1] = hi - (1 << 32) if hi >= 1 << 31 else hi
+            desc.reserved[0], desc.reserved[1] = mask_to_reserved(self.single_mask)
         names = sorted(model.weights)
         arr = (_lib.umx_tensor * len(names))()
         keep = []
