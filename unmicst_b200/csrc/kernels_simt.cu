@@ -577,11 +577,9 @@ size_t first_conv_smem_bytes(int cin, int ks, int cout) {
 
 template <int CIN, int KS>
 static cudaError_t launch_first(const FirstParams& p, unsigned grid, size_t sm, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
+    if (sm > 48 * 1024) {       // per device and per call: handles on different GPUs share this process
         cudaError_t e = cudaFuncSetAttribute(first_conv_kernel<CIN, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     first_conv_kernel<CIN, KS><<<grid, 256, sm, s>>>(p);
     return cudaGetLastError();
