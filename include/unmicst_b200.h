@@ -166,6 +166,11 @@ int64_t umx_launch_count(umx_handle* h);
 void* umx_host_alloc(int64_t bytes);
 void  umx_host_free(void* p);
 
+/* Host-only: TIFF 6.0 LZW decoder for the channel-page reader (the codec tifffile / imagecodecs give the reference's
+ * skio.imread(img_num=...) / tifffile.imread(key=...) calls, UnMicst1-5.py:794-797).  Returns the bytes written
+ * (at most dst_capacity), or a negative UMX_E* code for a corrupt stream.  Needs no GPU. */
+int64_t umx_tiff_lzw_decode(const uint8_t* src, int64_t src_bytes, uint8_t* dst, int64_t dst_capacity);
+
 const char* umx_last_error(void);
 const char* umx_version(void);
 

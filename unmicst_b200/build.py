@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB_PATH = os.path.join(CSRC, "libunmicst_b200.so")
 
-SOURCES = ["umx_api.cu", "kernels_simt.cu", "kernels_tc.cu"]
+SOURCES = ["umx_api.cu", "kernels_simt.cu", "kernels_tc.cu", "tiff_codec.cu"]
 HEADERS = ["umx_kernels.cuh", "umx_internal.h", "umx_tc.cuh", os.path.join(INCLUDE, "unmicst_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

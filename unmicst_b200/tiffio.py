@@ -5,12 +5,14 @@ scikit-image: reading ONE channel page of a (OME-)TIFF (UnMicst1-5.py:794-797,
 ``skio.imread(img_num=...)`` / ``tifffile.imread(key=...)``: the page index in the main IFD
 chain, SubIFD pyramids ignored) and writing uncompressed uint8 pages into a BigTIFF with
 append semantics (``skimage.io.imsave(..., bigtiff=True, append=...)``, UnMicst1-5.py:852-862).
-Uncompressed strips/tiles are read straight with numpy; anything else goes through PIL.
+Strips and tiles, uncompressed / Deflate / LZW, with or without the horizontal predictor, are decoded here
+(Deflate by zlib, LZW by the library's host-side decoder); anything else (JPEG, multi-sample) goes through PIL.
 """
 from __future__ import annotations
 
 import os
 import struct
+import zlib
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -22,6 +24,8 @@ _TYPE_SIZE = {1: 1, 2: 1, 3: 2, 4: 4, 5: 8, 6: 1, 7: 1, 8: 2, 9: 4, 10: 8, 11: 4
 T_WIDTH, T_LENGTH, T_BITS, T_COMPRESSION, T_PHOTOMETRIC, T_DESCRIPTION = 256, 257, 258, 259, 262, 270
 T_STRIP_OFFSETS, T_SPP, T_ROWS_PER_STRIP, T_STRIP_COUNTS, T_PLANAR = 273, 277, 278, 279, 284
 T_TILE_W, T_TILE_L, T_TILE_OFFSETS, T_TILE_COUNTS, T_SAMPLE_FORMAT = 322, 323, 324, 325, 339
+T_PREDICTOR = 317
+C_NONE, C_LZW, C_DEFLATE, C_DEFLATE_OLD = 1, 5, 8, 32946
 
 
 class TiffError(ValueError):
@@ -103,40 +107,70 @@ class _Reader:
                 return tags
         raise IndexError(f"{self.path}: page {page} out of range")
 
+    def _segment(self, off: int, nbytes: int, comp: int, rows: int, cols: int, dt: np.dtype, predictor: int) -> np.ndarray:
+        """One strip or tile -> [rows, cols] samples in native byte order."""
+        self.f.seek(off)
+        raw = self.f.read(nbytes)
+        want = rows * cols * dt.itemsize
+        if comp in (C_DEFLATE, C_DEFLATE_OLD):
+            raw = zlib.decompress(raw)
+        elif comp == C_LZW:
+            from ._lib import lib
+            out = np.empty(want, dtype=np.uint8)
+            src = np.frombuffer(raw, dtype=np.uint8)
+            n = lib().umx_tiff_lzw_decode(src.ctypes.data, src.size, out.ctypes.data, out.size)
+            if n < 0:
+                raise TiffError(f"{self.path}: corrupt LZW data")
+            raw = out[:n].tobytes()
+        if len(raw) < want:
+            raise TiffError(f"{self.path}: segment holds {len(raw)} of {want} bytes")
+        a = np.frombuffer(raw, dtype=dt, count=rows * cols).reshape(rows, cols).astype(dt.newbyteorder("="))
+        if predictor == 2:       # horizontal differencing, modulo the sample width
+            a = np.cumsum(a, axis=1, dtype=a.dtype)
+        return a
+
     def read_page(self, page: int) -> Optional[np.ndarray]:
-        """Decode an uncompressed single-sample page, or None if the layout needs a full codec."""
+        """Decode a single-sample page (strips or tiles; uncompressed, Deflate or LZW; optional horizontal
+        predictor), or None if the layout needs a full codec."""
         t = self.page_tags(page)
         w, h = t[T_WIDTH][0], t[T_LENGTH][0]
         bits = t.get(T_BITS, (1,))[0]
         spp = t.get(T_SPP, (1,))[0]
         comp = t.get(T_COMPRESSION, (1,))[0]
         fmt = t.get(T_SAMPLE_FORMAT, (1,))[0]
-        if comp != 1 or spp != 1 or bits not in (8, 16, 32, 64):
+        predictor = t.get(T_PREDICTOR, (1,))[0]
+        if comp not in (C_NONE, C_LZW, C_DEFLATE, C_DEFLATE_OLD) or spp != 1 or bits not in (8, 16, 32, 64):
             return None
         kind = {1: "u", 2: "i", 3: "f"}.get(fmt)
         if kind is None or (kind == "f" and bits < 32):
             return None
+        if predictor not in (1, 2) or (predictor == 2 and kind == "f"):
+            return None
         dt = np.dtype(f"{self.e}{kind}{bits // 8}")
         out = np.empty((h, w), dtype=dt.newbyteorder("="))
-        f = self.f
         if T_TILE_OFFSETS in t:
             tw, tl = t[T_TILE_W][0], t[T_TILE_L][0]
-            offs = t[T_TILE_OFFSETS]
+            offs, counts = t[T_TILE_OFFSETS], t.get(T_TILE_COUNTS)
             across = -(-w // tw)
             for i, off in enumerate(offs):
                 r0, c0 = (i // across) * tl, (i % across) * tw
-                f.seek(off)
-                tile = np.frombuffer(f.read(tw * tl * dt.itemsize), dtype=dt).reshape(tl, tw)
+                if r0 >= h:
+                    break
+                nbytes = counts[i] if counts else tw * tl * dt.itemsize
+                if nbytes == 0:                      # sparse (never written) tile
+                    out[r0:r0 + tl, c0:c0 + tw] = 0
+                    continue
+                tile = self._segment(off, nbytes, comp, tl, tw, dt, predictor)
                 rr, cc = min(tl, h - r0), min(tw, w - c0)
                 out[r0:r0 + rr, c0:c0 + cc] = tile[:rr, :cc]
         else:
             rps = min(t.get(T_ROWS_PER_STRIP, (h,))[0], h)
-            offs = t[T_STRIP_OFFSETS]
+            offs, counts = t[T_STRIP_OFFSETS], t.get(T_STRIP_COUNTS)
             for i, off in enumerate(offs):
                 r0 = i * rps
                 rr = min(rps, h - r0)
-                f.seek(off)
-                out[r0:r0 + rr] = np.frombuffer(f.read(rr * w * dt.itemsize), dtype=dt).reshape(rr, w)
+                nbytes = counts[i] if counts else rr * w * dt.itemsize
+                out[r0:r0 + rr] = self._segment(off, nbytes, comp, rr, w, dt, predictor)
         return out
 
 
