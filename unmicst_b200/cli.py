@@ -131,7 +131,7 @@ def run_tool(tool: str, argv: Optional[List[str]] = None) -> int:
     model_dir = resolve_model_dir(args.model, args.modelsDir)
     devices = pick_devices(args.GPU, args.gpus)
     print("Using GPU " + (str(devices[0]) if len(devices) == 1 else str(devices)))
-    precision = "default" if args.precision == "auto" else args.precision
+    precision = args.precision          # "auto" calibrates against the split mode on probe tiles (engine.Engine)
     UNet2D.singleImageInferenceSetup(model_dir, devices if len(devices) > 1 else devices[0], args.mean, args.std,
                                      precision=precision)
     try:
