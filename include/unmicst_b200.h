@@ -166,6 +166,11 @@ int64_t umx_launch_count(umx_handle* h);
 void* umx_host_alloc(int64_t bytes);
 void  umx_host_free(void* p);
 
+/* Host-only: text description (one line per op) of the plan umx_create would build for this model: graph
+ * construction as in UNet2D.setup (UnMicst1-5.py:55-237, UnMicst.py:51-187), BN folding, the raw-input rewrite and
+ * the kernel family of every op.  Needs no GPU.  Returns characters written or a negative UMX_E* code. */
+int64_t umx_describe_plan(const umx_model_desc* desc, const umx_tensor* weights, int32_t n_weights, char* out, int64_t capacity);
+
 /* Host-only: TIFF 6.0 LZW decoder for the channel-page reader (the codec tifffile / imagecodecs give the reference's
  * skio.imread(img_num=...) / tifffile.imread(key=...) calls, UnMicst1-5.py:794-797).  Returns the bytes written
  * (at most dst_capacity), or a negative UMX_E* code for a corrupt stream.  Needs no GPU. */

@@ -65,6 +65,7 @@ SYMBOLS = {
     "umx_debug_buffer": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_int32, C.c_void_p, C.c_int64]),
     "umx_host_alloc": (C.c_void_p, [C.c_int64]),
     "umx_host_free": (None, [C.c_void_p]),
+    "umx_describe_plan": (C.c_int64, [C.POINTER(umx_model_desc), C.POINTER(umx_tensor), C.c_int32, C.c_char_p, C.c_int64]),
     "umx_tiff_lzw_decode": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
     "umx_last_error": (C.c_char_p, []),
     "umx_version": (C.c_char_p, []),

@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <memory>
 
 #include "umx_internal.h"
 
@@ -1253,6 +1254,71 @@ int umx_infer_image(umx_handle* h, const void* img, int32_t dtype, int32_t n_pla
         drain_profile(h);
     }
     return UMX_OK;
+}
+
+// Host-only: the op list umx_create would build for this model (graph construction, BN folding, raw-input
+// rewrite, which kernel family runs each op), one line per op.  Needs no GPU: for tests and for inspecting a
+// checkpoint.  Returns the number of characters written (excluding the terminator) or a negative UMX_E* code.
+int64_t umx_describe_plan(const umx_model_desc* desc, const umx_tensor* weights, int32_t n_weights, char* out, int64_t capacity) {
+    if (!desc || !out || capacity <= 0 || (!weights && n_weights > 0)) { set_error("umx_describe_plan: bad argument"); return UMX_EINVAL; }
+    if (desc->abi_version != UMX_ABI_VERSION) { set_error("umx_describe_plan: ABI version %d != %d", desc->abi_version, UMX_ABI_VERSION); return UMX_EINVAL; }
+    if (desc->graph != UMX_GRAPH_LEGACY && desc->graph != UMX_GRAPH_V2) { set_error("unknown graph %d", desc->graph); return UMX_EINVAL; }
+    const int S = desc->im_size;
+    if (S < 8 || (S & (S - 1)) || desc->n_layers < 1 || (S >> desc->n_layers) < 4 || desc->n_channels < 1 || desc->n_out0 < 1 ||
+        desc->feat_maps_fact < 1 || desc->n_extra_convs < 0 || desc->n_classes < 2 || desc->n_classes > 4) {
+        set_error("invalid hyper-parameters"); return UMX_EINVAL;
+    }
+    std::unique_ptr<umx_handle> h(new (std::nothrow) umx_handle());
+    if (!h) { set_error("out of host memory"); return UMX_ENOMEM; }
+    h->desc = *desc;
+    h->S = S; h->C = desc->n_channels; h->K = desc->n_classes; h->L = desc->n_layers;
+    h->margin = S / 8; h->sub = S - 2 * h->margin;
+    h->chan = {desc->n_channels, desc->n_out0};
+    for (int i = 0; i < desc->n_layers; ++i) h->chan.push_back(h->chan.back() * desc->feat_maps_fact);
+    for (int i = 0; i < n_weights; ++i) {
+        const umx_tensor& t = weights[i];
+        if (!t.name || !t.data || t.ndim < 1 || t.ndim > 4) { set_error("weights[%d] malformed", i); return UMX_EINVAL; }
+        HostTensor ht;
+        for (int d = 0; d < t.ndim; ++d) ht.shape.push_back(t.shape[d]);
+        ht.data.assign(t.data, t.data + ht.numel());
+        h->tensors[t.name] = std::move(ht);
+    }
+    int rc = build_plan(h.get());
+    if (rc != UMX_OK) return rc;
+    h->precision = desc->precision == UMX_PREC_DEFAULT ? UMX_PREC_SPLIT3 : desc->precision;
+    if (h->precision == UMX_PREC_MIXED) h->single_mask = (uint64_t)(uint32_t)desc->reserved[0] | ((uint64_t)(uint32_t)desc->reserved[1] << 32);
+    if (h->precision < UMX_PREC_FP32 || h->precision > UMX_PREC_MIXED) { set_error("unknown precision %d", desc->precision); return UMX_EINVAL; }
+    rc = rewrite_narrow_sources(h.get());
+    if (rc != UMX_OK) return rc;
+    std::string text;
+    char line[512];
+    for (size_t i = 0; i < h->ops.size(); ++i) {
+        const Op& op = h->ops[i];
+        if (op.kind == OP_TAPS) {
+            const Buffer& ob = h->bufs[op.out_buf];
+            snprintf(line, sizeof line, "%zu taps %s src=%s k=%d out=%dx%dx%d\n", i, op.name.c_str(), h->bufs[op.taps_src].name.c_str(), op.taps_k, ob.h, ob.w, ob.c);
+        } else if (op.kind == OP_TOP) {
+            snprintf(line, sizeof line, "%zu top %s src=%s cin=%d k=%d\n", i, op.name.c_str(), h->bufs[op.top_src].name.c_str(), op.tp.cin, op.tp.k);
+        } else {
+            const int mode = tc_mode_of(h.get(), op);
+            const char* family = mode != TC_NONE ? "tensor" : (first_eligible(h.get(), op) ? "first" : "simt");
+            const Buffer& ob = h->bufs[op.out_buf];
+            std::string terms;
+            for (auto& t : op.spec.terms) {
+                terms += " [k=" + std::to_string(t.k) + " " + h->bufs[t.src0].name + ":" + std::to_string(h->bufs[t.src0].c);
+                if (t.src1 >= 0) terms += "|" + h->bufs[t.src1].name + ":" + std::to_string(h->bufs[t.src1].c);
+                terms += "]";
+            }
+            snprintf(line, sizeof line, "%zu conv %s %s mode=%d planes=%d%s%s%s%s out=%dx%dx%d flops=%.0f terms=%s\n", i, op.name.c_str(), family, mode,
+                     mode != TC_NONE ? op_planes(h.get(), op) : 0, op.spec.transpose ? " transpose" : "", op.spec.pool ? " pool" : "",
+                     op.spec.has_bias ? " bias" : "", op.spec.has_post ? " post" : "", ob.h, ob.w, ob.c, op.flops_per_tile, terms.c_str());
+        }
+        text += line;
+    }
+    const int64_t n = std::min<int64_t>((int64_t)text.size(), capacity - 1);
+    memcpy(out, text.data(), (size_t)n);
+    out[n] = 0;
+    return n;
 }
 
 }  // extern "C"

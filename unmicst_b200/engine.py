@@ -94,6 +94,38 @@ def mask_to_reserved(mask: int) -> Tuple[int, int]:
     return tuple(w - (1 << 32) if w >= 1 << 31 else w for w in words)
 
 
+def describe_plan(model: Model, precision: str = "default", single_mask: int = 0) -> List[str]:
+    """The op list the library would build for ``model`` (host-only ``umx_describe_plan``, no GPU needed): one line per
+    op with its kernel family (tensor / first / simt), tensor-path mode, operand planes, sources and FLOPs per tile."""
+    hp = model.hp
+    desc = _lib.umx_model_desc()
+    desc.abi_version = _lib.UMX_ABI_VERSION
+    desc.graph = {LEGACY: _lib.UMX_GRAPH_LEGACY, V2: _lib.UMX_GRAPH_V2}[model.variant]
+    desc.im_size, desc.n_channels, desc.n_classes = int(hp["imSize"]), int(hp["nChannels"]), int(hp["nClasses"])
+    desc.n_out0, desc.n_layers = int(hp["nOut0"]), int(hp["nLayers"])
+    desc.feat_maps_fact, desc.down_samp_fact = int(hp["featMapsFact"]), int(hp["downSampFact"])
+    desc.ks, desc.n_extra_convs = int(hp["ks"]), int(hp["nExtraConvs"])
+    desc.precision = _lib.PRECISIONS[precision]
+    if precision == "mixed":
+        desc.reserved[0], desc.reserved[1] = mask_to_reserved(single_mask)
+    names = sorted(model.weights)
+    arr = (_lib.umx_tensor * len(names))()
+    keep = []
+    for i, n in enumerate(names):
+        a = np.ascontiguousarray(model.weights[n], dtype=np.float32)
+        keep.append(a)
+        arr[i].name = n.encode()
+        arr[i].data = a.ctypes.data_as(C.POINTER(C.c_float))
+        arr[i].ndim = a.ndim
+        for d in range(a.ndim):
+            arr[i].shape[d] = a.shape[d]
+    buf = C.create_string_buffer(1 << 16)
+    n = lib().umx_describe_plan(C.byref(desc), arr, len(names), buf, len(buf))
+    if n < 0:
+        check(int(n))
+    return buf.value.decode().splitlines()
+
+
 class Engine:
     """precision: 'default'/'split3' (fp16 hi/lo split, ~fp32 accurate, always within the 2e-3 contract),
     'single' (one fp16 MMA per product: ~3x less tensor work, accuracy depends on how steep the
