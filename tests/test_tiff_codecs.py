@@ -32,7 +32,9 @@ def test_pillow_written_files_decode_natively(tmp_path, dtype, mode, compression
     from PIL import Image
     a = _image(211, 333, dtype, seed=3)
     p = tmp_path / f"{mode.replace(';', '')}_{compression}.tif"
-    Image.fromarray(a, mode=mode).save(p, compression=compression)
+    im = Image.fromarray(a)
+    assert im.mode == mode
+    im.save(p, compression=compression)
     got = _native(p)
     assert got is not None and got.dtype == dtype
     assert np.array_equal(got, a)
@@ -43,7 +45,7 @@ def test_pillow_lzw_with_horizontal_predictor(tmp_path):
     from PIL import Image
     a = _image(97, 260, np.uint8, seed=4)
     p = tmp_path / "pred.tif"
-    Image.fromarray(a, mode="L").save(p, compression="tiff_lzw", tiffinfo={317: 2})
+    Image.fromarray(a).save(p, compression="tiff_lzw", tiffinfo={317: 2})
     r = tiffio._Reader(str(p))
     tags = r.page_tags(0)
     r.close()
