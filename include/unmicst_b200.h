@@ -96,15 +96,29 @@ typedef struct umx_premap {
 typedef struct umx_opts {
     int32_t tile_row0;       /* band of PI2D tile rows [tile_row0, tile_row1) this call owns; */
     int32_t tile_row1;       /* tile_row1 <= 0 means "to the last tile row"                    */
-    int32_t precision;       /* UMX_PREC_* override for this call (0 = handle default)         */
+    int32_t precision;       /* 0, or the handle's own UMX_PREC_* (a different value is refused with UMX_EINVAL: the    */
+                             /* arithmetic is fixed when the handle is built; make a second handle for a check pass)    */
     int32_t flags;           /* UMX_F_*                                                        */
-    const umx_premap* premap;/* NULL = samples are already the float image the network sees   */
+    const umx_premap* premap;/* NULL = samples are already the float image the network sees (one map, or one per plane) */
     int64_t out_plane_stride;/* elements between class planes of out_u8/out_f32; 0 = H*W       */
     int32_t out_row_base;    /* image row that out_* row 0 corresponds to (band-local buffers) */
-    int32_t reserved[5];
+    int32_t infer_h;         /* --scalingFactor: run the network on skimage.transform.resize(img, (infer_h, infer_w))  */
+    int32_t infer_w;         /* (UnMicst1-5.py:813-815), resampled on the fly from the H x W samples; 0 = H / W        */
+    int32_t reserved[3];
 } umx_opts;
 
-#define UMX_F_NO_SYNC  1     /* return without waiting for the device (outputs must be device/pinned) */
+#define UMX_F_NO_SYNC    1   /* return without waiting for the device (outputs must be device/pinned) */
+#define UMX_F_PREMAP_PER_PLANE 4  /* umx_opts.premap points to one umx_premap per network input channel (unmicst-duo stretches each channel  */
+                                  /* with its own min/max, UnMicst2.py:760-788) instead of one shared map                          */
+#define UMX_F_CONTINUE   8   /* this call continues the image of the previous call on this handle (same image and options,   */
+                             /* tile_row0 == the previous tile_row1): the tile row above the seam is still on the device and  */
+                             /* is reused instead of recomputed — how a caller streams a slide band by band (e.g. into a     */
+                             /* BigTIFF writer, UnMicst1-5.py:852-862) at no extra cost                                      */
+#define UMX_F_STITCH_REPLACE 16 /* PI2D mode 'replace' (PartitionOfImage.py:99-100): in overlaps the tile patched last (row-major order) */
+                                /* wins and no ramp weights are applied; default is 'accumulate' (:95-98, what the CLI uses)           */
+#define UMX_F_CLI_QUANT  2   /* out_u8 = the page the reference CLI writes (UnMicst1-5.py:848-853): uint8(255*p), resize back */
+                             /* to the H x W grid of img when infer_h/infer_w differ, then uint8(255*x) a second time;       */
+                             /* out_u8 is then [K][H][W] (rows of umx_band_out_rows for a band); out_f32 must be NULL        */
 
 /* Per-kernel timing gathered with CUDA events on the handle's stream. */
 typedef struct umx_prof_entry {
@@ -130,7 +144,8 @@ int umx_create(const umx_model_desc* desc, const umx_tensor* weights, int32_t n_
 void umx_destroy(umx_handle* h);
 
 /* Session.run(UNet2D.nn, {tfData: tiles, tfTraining: 0}) (UnMicst1-5.py:704):
- * tiles [n,S,S,C] fp32 NHWC -> probs [n,S,S,K] fp32 softmax.  Any n >= 0. */
+ * tiles [n,S,S,C] fp32 NHWC -> probs [n,S,S,K] fp32 softmax.  Any n >= 0.
+ * `precision`: 0 or the handle's own UMX_PREC_* (anything else: UMX_EINVAL, see umx_opts.precision). */
 int umx_forward_tiles(umx_handle* h, const float* tiles_nhwc, int32_t n_tiles, float* probs_nhwc,
                       int32_t precision);
 
@@ -144,8 +159,35 @@ int umx_infer_image(umx_handle* h, const void* img, int32_t dtype, int32_t n_pla
                     int64_t plane_stride, double mean, double std_dev,
                     uint8_t* out_u8, float* out_f32, const umx_opts* opts);
 
+/* One image of a umx_infer_images batch: the arguments of umx_infer_image, per image. */
+typedef struct umx_image {
+    const void* img;         /* [n_planes][H][W] samples */
+    int32_t dtype, n_planes, H, W;
+    int64_t plane_stride;    /* elements; 0 = H*W */
+    const umx_premap* premap;/* NULL or ONE map for this image */
+    uint8_t* out_u8;         /* [K][H][W] floor(255 p) (twice quantised with UMX_F_CLI_QUANT) or NULL */
+    float*   out_f32;        /* [K][H][W] or NULL */
+} umx_image;
+
+/* Many small images through one resident model — the TMA "dearray" loop of batchUNet2DTMACycif.py:539-569, where the
+ * reference runs singleImageInference core by core.  Tiles of as many images as fit a launch group share every network
+ * launch, so small cores fill the GPU; results equal umx_infer_image per image bit for bit.  flags: UMX_F_CLI_QUANT. */
+int umx_infer_images(umx_handle* h, const umx_image* images, int32_t n_images, double mean, double std_dev, int32_t flags);
+
 /* Image rows [row0,row1) produced by a tile-row band (host-side helper for sharding). */
 int umx_band_rows(umx_handle* h, int32_t H, int32_t tile_row0, int32_t tile_row1, int32_t* row0, int32_t* row1);
+
+/* Same for UMX_F_CLI_QUANT output when the network runs at infer_h rows and the pages are resized back to raw_h rows:
+ * the raw-grid rows [row0,row1) whose resize window lies inside what the band computes (bands stay disjoint and
+ * complete, and need no exchange).  With raw_h == infer_h this equals umx_band_rows. */
+int umx_band_out_rows(umx_handle* h, int32_t infer_h, int32_t tile_row0, int32_t tile_row1, int32_t raw_h,
+                      int32_t* row0, int32_t* row1);
+
+/* min and max of skimage.transform.resize(img_as_float(plane), (out_h, out_w)) — rescale_intensity's in_range for the
+ * tools that stretch the resized image (UnMicst.py:627-631) — computed on the device; plane: H x W samples, host or
+ * device memory.  in_scale = img_as_float's factor (1/65535, 1/255 or 1). */
+int umx_resample_minmax(umx_handle* h, const void* plane, int32_t dtype, int32_t H, int32_t W, int32_t out_h, int32_t out_w,
+                        double in_scale, double* min_out, double* max_out);
 
 /* Use the caller's CUDA stream (cudaStream_t as an integer) for all compute; 0 = library stream. */
 int umx_set_stream(umx_handle* h, uint64_t cuda_stream);

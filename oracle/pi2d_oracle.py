@@ -95,7 +95,7 @@ def analytic_count(g: TileGrid) -> np.ndarray:
 
 def infer_image(image: np.ndarray, forward: Callable[[np.ndarray], np.ndarray], patch: int, n_channels: int,
                 mean: float, std: float, batch: int, accum_dtype=np.float16,
-                classes: List[int] = None) -> np.ndarray:
+                classes: List[int] = None, mode: str = "accumulate") -> np.ndarray:
     """singleImageInference for all requested classes in ONE network pass per batch.
 
     ``forward`` maps [B,P,P,C] float32 -> [B,P,P,K] float32 (the Session.run of
@@ -104,6 +104,7 @@ def infer_image(image: np.ndarray, forward: Callable[[np.ndarray], np.ndarray], 
     (hp['batchSize'], :697-703).  Stitching follows patchOutput/getValidOutput with
     ``accum_dtype`` storage (float16 = the reference's behaviour; float32/float64 =
     the variant the shipped goldens actually agree with best).
+    ``mode`` 'replace' (PartitionOfImage.py:99-100, never used by the CLI): Output[tile] = P, no weights, no divide.
     Returns [K', H, W] in accum_dtype, K' = len(classes) (all classes by default)."""
     rows, cols = image.shape[-2:]
     g = tile_grid(rows, cols, patch, int(patch / 8))
@@ -131,11 +132,17 @@ def infer_image(image: np.ndarray, forward: Callable[[np.ndarray], np.ndarray], 
                 out = np.zeros((len(classes), g.frame_rows, g.frame_cols), dtype=accum_dtype)
             for k, tt in enumerate(pending):
                 r0, c0 = g.origin(tt)
+                if mode == "replace":
+                    for ci, cls in enumerate(classes):
+                        out[ci, r0:r0 + patch, c0:c0 + patch] = probs[k, :, :, cls]
+                    continue
                 count[r0:r0 + patch, c0:c0 + patch] += w
                 for ci, cls in enumerate(classes):
                     out[ci, r0:r0 + patch, c0:c0 + patch] += np.multiply(probs[k, :, :, cls], w)
             pending = []
     m = g.margin
+    if mode == "replace":
+        return out[:, m:m + rows, m:m + cols]
     c = count[m:m + rows, m:m + cols]
     return np.divide(out[:, m:m + rows, m:m + cols], c)
 

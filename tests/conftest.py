@@ -15,6 +15,24 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _gpu_available() -> bool:
+    try:
+        from unmicst_b200 import _lib
+        return _lib.lib().umx_device_count() > 0
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """`pytest tests` on a CPU-only host: the gpu-marked tests are skipped (they only run with a CUDA device)."""
+    if _gpu_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device visible (gpu-marked tests run on the B200 box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN

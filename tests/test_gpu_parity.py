@@ -112,6 +112,31 @@ def test_legacy_auto_rejects_plain_single(sample_raw, nuclei_model):
     _check_probs(got, _oracle_fw(nuclei_model)(tiles))
 
 
+def test_auto_on_steep_weights_and_image_tiles(sample_raw):
+    """`auto` as the bench and the CLI run it: calibrated on tiles cut from the image being processed (borders with
+    their -mean/std padding included), weights as steep as the real models' (max|logit| ~ 20).
+    One MMA per product everywhere is then outside the contract; the error-budgeted per-layer choice must stay inside
+    it against the ORACLE, on the calibration tiles and on tiles it has never seen."""
+    from unmicst_b200.engine import AUTO_TOLERANCE, PreMap, sample_probe_tiles
+    m = modelzoo.synthetic_model("nucleiDAPI1-5", seed=0, logit_gain=22.0)
+    pm = PreMap(in_scale=1.0 / 65535)
+    tiles = sample_probe_tiles(sample_raw, 64, 1, m.mean, m.std, pm, n=48)
+    unseen = sample_probe_tiles(sample_raw, 64, 1, m.mean, m.std, pm, n=40, seed=5)[8:]
+    taps = {}
+    want = unet_oracle.forward(m.weights, m.hp, m.variant, tiles, taps=taps)
+    assert np.abs(taps["logits"]).max() > 12
+    with _engine(m, precision="auto", probe_tiles=tiles) as e:
+        rep = e.auto_report
+        got, got_unseen = e.forward_tiles(tiles), e.forward_tiles(unseen)
+        assert e.precision == rep["chosen"]
+    assert rep["probe_tiles"] == len(tiles) and rep["budget"] == AUTO_TOLERANCE
+    if rep["chosen"] == "mixed":
+        assert rep["single_layers"] and rep["mixed_vs_split3_max_abs_dp"] <= AUTO_TOLERANCE
+        assert all(l["dp_alone"] >= 0 and l["split_ms"] > 0 for l in rep["layers"])
+    _check_probs(got, want)
+    _check_probs(got_unseen, _oracle_fw(m)(unseen))
+
+
 def test_mixed_precision_masks_v2():
     """Any subset of layers may run with one MMA per product: all-zero mask == split3 bit for bit, a partial mask and
     the full mask stay within the contract."""

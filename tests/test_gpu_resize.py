@@ -1,0 +1,195 @@
+"""-m gpu: --scalingFactor on the device and the other driver paths added around the hot path:
+resize of the input inside the tile gather, resize-back + second uint8 quantisation of the pages, band streaming,
+many-images batches, PI2D 'replace' mode.  All through the C-ABI, against the oracle restatements.
+
+Tolerances: network input exact to float32 rounding; probabilities max|dp| <= 2e-3; uint8 pages +-1 level."""
+import numpy as np
+import pytest
+
+from oracle import pi2d_oracle, prepost_oracle, unet_oracle
+from unmicst_b200 import modelzoo
+
+pytestmark = pytest.mark.gpu
+
+TOL_P = 2e-3
+
+
+def _engine(model, **kw):
+    from unmicst_b200.engine import Engine
+    return Engine(model, device=0, **kw)
+
+
+def _fw(model):
+    return lambda x: unet_oracle.forward(model.weights, model.hp, model.variant, x)
+
+
+@pytest.fixture(scope="module")
+def solo():
+    return modelzoo.synthetic_model("nucleiDAPI1-5", seed=0)
+
+
+@pytest.mark.parametrize("factor", [2.0, 1.5, 0.5, 0.37])
+def test_gathered_tiles_of_a_resized_image_are_exact(sample_raw, solo, factor):
+    """u16 samples -> img_as_float -> skimage.transform.resize -> (x-mean)/std -> float32, all in the gather kernel,
+    equals the oracle's tiles of prepare_solo(raw, factor) (UnMicst1-5.py:813-816 + :700)."""
+    from unmicst_b200.engine import PreMap
+    crop = sample_raw[100:260, 200:420]
+    cells = prepost_oracle.prepare_solo(crop, factor)
+    g = pi2d_oracle.tile_grid(cells.shape[0], cells.shape[1], 64, 8)
+    frame = pi2d_oracle.pad_frame(cells, g)
+    want = np.stack([(pi2d_oracle.cut_tile(frame, g, i) - solo.mean) / solo.std for i in range(g.num_tiles)])[..., None].astype(np.float32)
+    with _engine(solo, max_batch_tiles=max(64, g.num_tiles)) as e:
+        e.infer_image(crop, premap=PreMap(in_scale=1.0 / 65535), infer_shape=cells.shape)
+        got = e.debug_buffer("input", g.num_tiles, (64, 64, 1))
+    d = np.abs(got - want)
+    # upscaling follows ndimage.zoom operation for operation (bit-exact float64 -> identical float32); the Gaussian
+    # pre-filter of a shrink is summed in one pass instead of two, which can move a float64 by an ulp
+    assert d.max() <= (0 if factor == 2.0 else 2.4e-7 * np.abs(want).max())
+    assert (d > 0).mean() <= (0 if factor == 2.0 else 1e-3)
+
+
+@pytest.mark.parametrize("factor", [2.0, 0.5])
+def test_scaling_factor_pages_match_the_oracle_pipeline(sample_raw, solo, factor):
+    """resize -> tiles -> UNet -> stitch -> uint8 -> resize back -> uint8 (UnMicst1-5.py:813-853) in one call."""
+    from unmicst_b200.engine import PreMap
+    crop = sample_raw[100:260, 200:420]
+    cells = prepost_oracle.prepare_solo(crop, factor)
+    pm = pi2d_oracle.infer_image(cells, _fw(solo), 64, 1, solo.mean, solo.std, 32, accum_dtype=np.float64)
+    with _engine(solo) as e:
+        _, f32 = e.infer_image(crop, premap=PreMap(in_scale=1.0 / 65535), infer_shape=cells.shape, want_u8=False, want_f32=True)
+        pages, _ = e.infer_image(crop, premap=PreMap(in_scale=1.0 / 65535), infer_shape=cells.shape, cli_quant=True)
+    assert f32.shape == (3,) + cells.shape and np.abs(f32 - pm).max() <= TOL_P
+    assert pages.shape == (3,) + crop.shape
+    for cls in range(3):
+        want = np.uint8(255 * prepost_oracle.resize(np.uint8(255 * pm[cls]), crop.shape))
+        assert np.abs(pages[cls].astype(int) - want.astype(int)).max() <= 1
+
+
+def test_resize_back_kernel_alone_is_exact_on_identical_input(solo):
+    """Feed the device the oracle's own uint8 maps through a band continuation trick is not possible, so check the
+    resize-back arithmetic via an image whose maps are known: at equal size UMX_F_CLI_QUANT is the LUT
+    uint8(255 * (v * 1/255)) of the reference's double quantisation."""
+    rng = np.random.default_rng(4)
+    img = rng.random((130, 90))
+    with _engine(solo) as e:
+        once, _ = e.infer_image(img)
+        twice, _ = e.infer_image(img, cli_quant=True)
+    assert np.array_equal(twice, np.uint8(255 * (once.astype(np.float64) * (1.0 / 255))))
+    assert np.abs(twice.astype(int) - once.astype(int)).max() <= 1
+
+
+def test_bands_with_scaling_reassemble_bit_exactly(sample_raw, solo):
+    from unmicst_b200.engine import PreMap, split_tile_rows, tile_geometry
+    crop = sample_raw[:300, :200]
+    shape = (600, 400)
+    pm = PreMap(in_scale=1.0 / 65535)
+    _, _, npr, _ = tile_geometry(shape[0], shape[1], 64)
+    with _engine(solo, max_batch_tiles=40) as e:
+        whole, _ = e.infer_image(crop, premap=pm, infer_shape=shape, cli_quant=True)
+        for parts in (2, 3, 5):
+            out = np.zeros_like(whole)
+            covered = np.zeros(crop.shape[0], dtype=int)
+            for band in split_tile_rows(npr, parts):
+                e.infer_image(crop, premap=pm, infer_shape=shape, cli_quant=True, tile_rows=band, out_u8=out)
+                r0, r1 = e.band_out_rows(shape[0], crop.shape[0], band)
+                covered[r0:r1] += 1
+            assert (covered == 1).all()
+            assert np.array_equal(out, whole)
+
+
+@pytest.mark.parametrize("scaled", [False, True])
+def test_streamed_bands_equal_one_call(sample_raw, solo, scaled):
+    """stream_image: bands continue each other on the device (UMX_F_CONTINUE), nothing recomputed, same bytes."""
+    from unmicst_b200.engine import PreMap
+    crop = sample_raw[:260, :300]
+    pm = PreMap(in_scale=1.0 / 65535)
+    shape = (520, 600) if scaled else None
+    with _engine(solo, max_batch_tiles=30) as e:
+        whole, _ = e.infer_image(crop, premap=pm, infer_shape=shape, cli_quant=True)
+        n0 = e.launch_count
+        e.infer_image(crop, premap=pm, infer_shape=shape, cli_quant=True)
+        one_call = e.launch_count - n0
+        out = np.zeros_like(whole)
+        n0 = e.launch_count
+        rows = 0
+        for r0, r1, buf in e.stream_image(crop, premap=pm, chunk_tile_rows=3, infer_shape=shape, cli_quant=True):
+            out[:, r0:r1] = buf
+            rows += r1 - r0
+        streamed = e.launch_count - n0
+    assert rows == crop.shape[0] and np.array_equal(out, whole)
+    # no seam row is recomputed: the extra launches are only the per-band gathers / stitches / tables
+    assert streamed <= one_call + 8 * (-(-((shape or crop.shape)[0] + 47) // 48 // 3) + 1)
+
+
+def test_many_images_per_launch_equal_single_calls(sample_raw, solo):
+    """umx_infer_images (TMA cores, batchUNet2DTMACycif.py:539-569): bit-identical to one call per image."""
+    from unmicst_b200.engine import PreMap
+    rng = np.random.default_rng(6)
+    cores = [sample_raw[a:a + h, b:b + w].copy() for a, b, h, w in ((0, 0, 100, 120), (50, 300, 64, 64), (200, 100, 150, 90),
+                                                                    (400, 400, 48, 200), (10, 500, 1, 1), (300, 0, 333, 410))]
+    pms = [PreMap(in_scale=1.0 / 65535) for _ in cores]
+    with _engine(solo, max_batch_tiles=64) as e:
+        n0 = e.launch_count
+        batch = e.infer_images(cores, pms)
+        batched = e.launch_count - n0
+        n0 = e.launch_count
+        singles = [e.infer_image(c, premap=p)[0] for c, p in zip(cores, pms)]
+        alone = e.launch_count - n0
+        f32 = e.infer_images(cores[:2], pms[:2], want_f32=True)
+        want0 = e.infer_image(cores[0], premap=pms[0], want_u8=False, want_f32=True)[1]
+    assert all(np.array_equal(a, b) for a, b in zip(batch, singles))
+    assert np.array_equal(f32[0], want0)
+    assert batched < alone                       # the five small cores shared network launches; the big one ran alone
+
+
+def test_replace_mode_matches_pi2d(solo):
+    rng = np.random.default_rng(9)
+    img = rng.random((150, 201))
+    with _engine(solo) as e:
+        _, got = e.infer_image(img, want_u8=False, want_f32=True, stitch_mode="replace")
+        with pytest.raises(ValueError):
+            e.infer_image(img, stitch_mode="average")
+    want = pi2d_oracle.infer_image(img, _fw(solo), 64, 1, solo.mean, solo.std, 32, accum_dtype=np.float64, mode="replace")
+    assert np.abs(got - want).max() <= TOL_P
+
+
+def test_per_channel_premaps_duo(sample_raw):
+    """unmicst-duo stretches each channel with its own range (UnMicst2.py:760-788): one PreMap per plane on the device
+    equals planes prepared on the host."""
+    from unmicst_b200.engine import PreMap
+    m = modelzoo.synthetic_model("nucleiDAPILAMIN", seed=0)
+    a = sample_raw[:200, :260]
+    b = (sample_raw[300:500, 100:360] // 3).astype(np.uint16)
+    pms = []
+    planes = []
+    for ch in (a, b):
+        f = ch.astype(np.float64) * (1.0 / 65535)
+        pms.append(PreMap(in_scale=1.0 / 65535, rescale=True, imin=float(f.min()), imax=float(f.max())))
+        planes.append(prepost_oracle.prepare_rescaled(ch))
+    with _engine(m) as e:
+        dev, _ = e.infer_image(np.stack([a, b]), premap=pms)
+        host, _ = e.infer_image(np.stack(planes))
+    assert np.array_equal(dev, host)
+
+
+def test_resample_minmax_matches_the_resized_image(sample_raw, solo):
+    crop = sample_raw[:200, :300]
+    with _engine(solo) as e:
+        for f in (2.0, 0.5, 1.0):
+            shape = (int(200 * f), int(300 * f))
+            lo, hi = e.resample_minmax(crop, shape, 1.0 / 65535)
+            r = prepost_oracle.resize(crop, shape)
+            assert abs(lo - r.min()) <= 1e-15 and abs(hi - r.max()) <= 1e-15
+
+
+def test_precision_override_is_refused_not_ignored(solo):
+    from unmicst_b200._lib import EngineError
+    rng = np.random.default_rng(1)
+    tiles = rng.normal(size=(2, 64, 64, 1)).astype(np.float32)
+    with _engine(solo, precision="split3") as e:
+        a = e.forward_tiles(tiles)
+        assert np.array_equal(e.forward_tiles(tiles, precision="split3"), a)      # naming the handle's own mode is fine
+        with pytest.raises(EngineError):
+            e.forward_tiles(tiles, precision="fp32")
+        with pytest.raises(EngineError):
+            e.infer_image(rng.random((70, 70)), precision="single")

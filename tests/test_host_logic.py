@@ -24,13 +24,25 @@ def test_reference_tile_counts():
     assert cnt(20000, 20000, 64) == 173889 and cnt(4096, 4096, 128) == 1849 and cnt(40000, 40000, 64) == 695556
 
 
-@pytest.mark.parametrize("npr,parts", [(417, 8), (9, 2), (3, 8), (1, 4), (100, 1)])
+@pytest.mark.parametrize("npr,parts", [(417, 8), (9, 2), (3, 8), (1, 4), (100, 1), (834, 8), (8, 8), (10, 8)])
 def test_band_split_is_a_partition(npr, parts):
-    bands = split_tile_rows(npr, parts)
-    assert bands[0][0] == 0 and bands[-1][1] == npr
-    assert all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
-    sizes = [b - a for a, b in bands]
-    assert min(sizes) >= 1 and max(sizes) - min(sizes) <= 1
+    for balance in (False, True):
+        bands = split_tile_rows(npr, parts, balance_seams=balance)
+        assert bands[0][0] == 0 and bands[-1][1] == npr
+        assert all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+        sizes = [b - a for a, b in bands]
+        assert min(sizes) >= 1
+        if balance:     # what a GPU computes = its rows + the recomputed seam row (all bands but the first)
+            comp = [n + (1 if i else 0) for i, n in enumerate(sizes)]
+            assert max(comp) - min(comp) <= 1
+        else:
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_band_split_417_rows_on_8_gpus_computes_53_each():
+    """20k x 20k solo = 417 tile rows; balanced with the seam row every GPU computes 53 (not 54)."""
+    bands = split_tile_rows(417, 8)
+    assert [b - a + (1 if i else 0) for i, (a, b) in enumerate(bands)] == [53] * 8
 
 
 def test_wrapper_converts_to_zero_based():
@@ -75,16 +87,54 @@ def _apply(arr, pm):
 
 
 def test_network_input_matches_oracle_preprocessing(sample_raw):
-    arr, pm = prepost.network_input(sample_raw, 1.0, stretch=True)
-    assert arr.dtype == np.uint16                                      # integers go to the GPU untouched
+    arr, pm, shape = prepost.network_input(sample_raw, 1.0, stretch=True)
+    assert arr.dtype == np.uint16 and shape is None                    # integers go to the GPU untouched
     assert np.array_equal(_apply(arr, pm), prepost_oracle.prepare_rescaled(sample_raw))
-    arr, pm = prepost.network_input(sample_raw, 1.0, stretch=False)
+    arr, pm, shape = prepost.network_input(sample_raw, 1.0, stretch=False)
     assert np.array_equal(_apply(arr, pm), prepost_oracle.prepare_solo(sample_raw))
     crop = sample_raw[:200, :300]
     for f in (2.0, 0.5):
-        arr, pm = prepost.network_input(crop, f, stretch=True, outlier=99.0)
-        assert arr.shape == (int(200 * f), int(300 * f))
-        assert np.allclose(_apply(arr, pm), prepost_oracle.prepare_rescaled(crop, f, 99.0), atol=1e-12)
+        # the samples stay raw; the resize happens on the GPU (tests/test_gpu_resize.py); the stretch range is the
+        # resized image's (UnMicst.py:627-631), here through the host path (no engine): percentile and plain max
+        for outlier in (99.0, -1):
+            arr, pm, shape = prepost.network_input(crop, f, stretch=True, outlier=outlier)
+            assert arr is crop or np.array_equal(arr, crop)
+            assert shape == (int(200 * f), int(300 * f))
+            resized = prepost_oracle.resize(crop, shape)
+            top = np.max(resized) if outlier == -1 else np.percentile(resized, outlier)
+            assert abs(pm.imin - resized.min()) <= 1e-15 and abs(pm.imax - top) <= 1e-15 and pm.rescale
+            want = prepost_oracle.prepare_rescaled(crop, f, outlier)
+            x = np.clip(resized, pm.imin, pm.imax)
+            assert np.allclose((x - pm.imin) / (pm.imax - pm.imin) * 0.983, want, atol=1e-12)
+
+
+def test_probe_tiles_equal_the_oracle_tiler(sample_raw):
+    """engine.sample_probe_tiles (calibration / bench parity probes) cuts the same network inputs as the reference's
+    tile loop (PartitionOfImage.py:49-82 + UnMicst1-5.py:700), also through a --scalingFactor resize."""
+    from unmicst_b200.engine import PreMap, probe_tile_indices, sample_probe_tiles, tile_geometry
+    crop = sample_raw[:150, :333]
+    for f in (1.0, 2.0):
+        cells = prepost_oracle.prepare_solo(crop, f)
+        g = pi2d_oracle.tile_grid(cells.shape[0], cells.shape[1], 64, 8)
+        frame = pi2d_oracle.pad_frame(cells, g)
+        _, _, npr, npc = tile_geometry(cells.shape[0], cells.shape[1], 64)
+        idx = probe_tile_indices(npr, npc, 12)
+        assert len(set(idx)) == len(idx) == min(12, npr * npc) and 0 in idx and npr * npc - 1 in idx
+        got = sample_probe_tiles(crop, 64, 1, 0.34, 0.25, PreMap(in_scale=1.0 / 65535), indices=idx,
+                                 infer_shape=None if f == 1.0 else cells.shape)
+        want = np.stack([(pi2d_oracle.cut_tile(frame, g, i) - 0.34) / 0.25 for i in idx])[..., None].astype(np.float32)
+        assert np.abs(got - want).max() <= (0 if f == 1.0 else 1e-6)
+
+
+def test_error_budgeted_layer_selection():
+    """engine.choose_single_mask: the subset with the largest saving whose errors, added in quadrature, fit the budget."""
+    from unmicst_b200.engine import choose_single_mask
+    errs = {1: 1e-4, 2: 5e-4, 3: 9e-4, 5: 2e-3}
+    costs = {1: 1.0, 2: 2.0, 3: 5.0, 5: 50.0}
+    assert choose_single_mask(errs, costs, 1e-3) == (1 << 1) | (1 << 3)         # {2,3} = 1.03e-3 is over; 5 never fits
+    assert choose_single_mask(errs, costs, 1e-5) == 0
+    assert choose_single_mask(errs, costs, 1.0) == 0b101110
+    assert choose_single_mask(errs, {1: 1.0, 2: 0.0, 3: 5.0, 5: 50.0}, 1.0) == 0b101010   # no saving, no bit
 
 
 def test_requantisation_table_and_preview(sample_raw, sample_goldens):
@@ -93,6 +143,29 @@ def test_requantisation_table_and_preview(sample_raw, sample_goldens):
     assert np.array_equal(prepost.back_to_raw_size(v, (16, 16)), want)
     assert np.abs(want.astype(int) - v.astype(int)).max() <= 1
     assert np.array_equal(prepost.preview_page(sample_raw), sample_goldens["raw"])
+
+
+def test_streamed_pages_fill_in_any_band_order(tmp_path):
+    """The K class maps leave the GPU band by band: BigTiffWriter.begin_pages reserves every page, rows land in place."""
+    rng = np.random.default_rng(3)
+    pages = rng.integers(0, 255, (3, 100, 77), dtype=np.uint8)
+    p = str(tmp_path / "bands.tif")
+    w = tiffio.BigTiffWriter(p)
+    w.begin_pages(3, 100, 77)
+    for r0, r1 in ((40, 100), (0, 17), (17, 40)):
+        for k in range(3):
+            w.write_page_rows(k, r0, pages[k, r0:r1])
+    w.end_pages()
+    w.write_page(pages[0][:50])                 # the preview page follows
+    w.close()
+    assert tiffio.count_pages(p) == 4
+    assert all(np.array_equal(tiffio.read_page(p, k), pages[k]) for k in range(3))
+    assert np.array_equal(tiffio.read_page(p, 3), pages[0][:50])
+    w = tiffio.BigTiffWriter(str(tmp_path / "short.tif"))
+    w.begin_pages(1, 10, 5)
+    w.write_page_rows(0, 0, np.zeros((4, 5), np.uint8))
+    with pytest.raises(tiffio.TiffError):
+        w.end_pages()                           # 6 rows never arrived
 
 
 def test_tiff_roundtrip_append_and_golden_pages(tmp_path, golden_dir, sample_goldens):

@@ -17,6 +17,10 @@ UMX_GRAPH_LEGACY, UMX_GRAPH_V2 = 0, 1
 UMX_U8, UMX_U16, UMX_F32, UMX_F64 = 0, 1, 2, 3
 UMX_PREC_DEFAULT, UMX_PREC_FP32, UMX_PREC_SPLIT3, UMX_PREC_SINGLE, UMX_PREC_MIXED = 0, 1, 2, 3, 4
 UMX_F_NO_SYNC = 1
+UMX_F_CLI_QUANT = 2
+UMX_F_PREMAP_PER_PLANE = 4
+UMX_F_CONTINUE = 8
+UMX_F_STITCH_REPLACE = 16
 
 PRECISIONS = {"default": UMX_PREC_DEFAULT, "fp32": UMX_PREC_FP32, "split3": UMX_PREC_SPLIT3, "single": UMX_PREC_SINGLE,
               "mixed": UMX_PREC_MIXED}
@@ -40,7 +44,12 @@ class umx_premap(C.Structure):
 class umx_opts(C.Structure):
     _fields_ = [("tile_row0", C.c_int32), ("tile_row1", C.c_int32), ("precision", C.c_int32), ("flags", C.c_int32),
                 ("premap", C.POINTER(umx_premap)), ("out_plane_stride", C.c_int64), ("out_row_base", C.c_int32),
-                ("reserved", C.c_int32 * 5)]
+                ("infer_h", C.c_int32), ("infer_w", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
+class umx_image(C.Structure):
+    _fields_ = [("img", C.c_void_p), ("dtype", C.c_int32), ("n_planes", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("plane_stride", C.c_int64), ("premap", C.POINTER(umx_premap)), ("out_u8", C.c_void_p), ("out_f32", C.c_void_p)]
 
 
 class umx_prof_entry(C.Structure):
@@ -57,7 +66,11 @@ SYMBOLS = {
     "umx_forward_tiles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
     "umx_infer_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                                   C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.POINTER(umx_opts)]),
+    "umx_infer_images": (C.c_int, [C.c_void_p, C.POINTER(umx_image), C.c_int32, C.c_double, C.c_double, C.c_int32]),
     "umx_band_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "umx_band_out_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "umx_resample_minmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double,
+                                      C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "umx_set_stream": (C.c_int, [C.c_void_p, C.c_uint64]),
     "umx_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "umx_profile_read": (C.c_int, [C.c_void_p, C.POINTER(umx_prof_entry), C.c_int32, C.c_int32]),

@@ -16,7 +16,9 @@ from __future__ import annotations
 
 import argparse
 import os
+import queue
 import sys
+import threading
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -76,8 +78,7 @@ def tool_parser(spec: ToolSpec) -> argparse.ArgumentParser:
 
 
 def resolve_model_dir(model: str, models_dir: Optional[str]) -> str:
-    roots = [models_dir, os.environ.get("UNMICST_MODELS"), os.path.join(REPO, "models"),
-             os.path.join(REPO, "tests", "golden", "models")]
+    roots = [models_dir, os.environ.get("UNMICST_MODELS"), os.path.join(REPO, "models")]
     for r in roots:
         if r and os.path.isdir(os.path.join(r, model)):
             return os.path.join(r, model)
@@ -160,20 +161,17 @@ def _process(spec: ToolSpec, args) -> int:
     raws = [prepost.coerce_raw(read_channel(image_path, ftype, c)) for c in chans]
     raw_shape = raws[0].shape
     raw_last = raws[-1]                                       # rawI is the last page read (UnMicst2.py:771,792)
-    prepared = [prepost.network_input(r, args.scalingFactor, spec.stretch, args.outlier) for r in raws]
+    # the raw samples go to the GPU untouched; img_as_float, resize (--scalingFactor) and the rescale_intensity stretch
+    # (each channel with its own min/max) happen in the gather kernel, the resize back and the second uint8
+    # quantisation in the output kernels (UnMicst1-5.py:813-821,848-853)
+    prepared = [prepost.network_input(r, args.scalingFactor, spec.stretch, args.outlier, engine=UNet2D.Engine) for r in raws]
+    infer_shape = prepared[0][2]
     if len(prepared) == 1:
-        image, premap = prepared[0]
-        planes = None
+        image, premap = prepared[0][0], prepared[0][1]
     else:
-        # duo: each channel is stretched with its own min/max; apply on the host per plane, feed float64
-        planes = []
-        for arr, pm in prepared:
-            x = arr.astype(np.float64) * pm.in_scale
-            if pm.rescale:
-                x = np.clip(x, pm.imin, pm.imax)
-                x = (x - pm.imin) / (pm.imax - pm.imin) * (pm.omax - pm.omin) + pm.omin
-            planes.append(x)
-        image, premap = np.stack(planes), None
+        if any(p[0].dtype != prepared[0][0].dtype or p[0].shape != raw_shape for p in prepared):
+            raise ValueError("the channel pages differ in size or sample type")
+        image, premap = np.stack([p[0] for p in prepared]), [p[1] for p in prepared]
 
     class_order = list(range(n_class)) if args.classOrder == -1 else list(args.classOrder)
     out_dir = args.outputPath if args.outputPath else parent + "//probability_maps"
@@ -182,28 +180,60 @@ def _process(spec: ToolSpec, args) -> int:
     if spec.qc_dir:
         os.makedirs(qc_dir, exist_ok=True)
     suffix = str(dapi + 1) if spec.one_based_names else str(dapi)
-
-    pm_u8 = UNet2D.singleImageInferenceAll(image, premap=premap, as_uint8=True)     # [K,H,W], one pass
-    page = lambda cls: prepost.back_to_raw_size(pm_u8[cls], raw_shape)
     preview = prepost.preview_page(raw_last)
+    H, W = raw_shape
 
+    # files and the class each of their pages holds; pages fill band by band while the GPU works on the next band
+    # (a writer thread drains a queue), then the preview pages are appended
     if args.stackOutput:
         prob_path = os.path.join(out_dir, f"{stem}_Probabilities_{suffix}.tif")
-        for i, cls in enumerate(class_order[::-1]):           # backwards in order to align with ilastik
-            pg = page(cls)
-            tiffio.imsave(prob_path, pg, append=i > 0)
-            if i == 1:
-                prev_path = os.path.join(qc_dir, f"{stem}_Preview_{suffix}.tif")
-                tiffio.imsave(prev_path, pg, append=False)
-                tiffio.imsave(prev_path, preview, append=True)
+        plan = [(prob_path, list(class_order[::-1]))]         # backwards in order to align with ilastik
+        if len(class_order) > 1:
+            plan.append((os.path.join(qc_dir, f"{stem}_Preview_{suffix}.tif"), [class_order[::-1][1]]))
     else:
         if len(class_order) < 3:
             raise ValueError("without --stackOutput the contours/nuclei pair needs a 3-class model "
                              "(the reference indexes classOrder[2] and fails too); use --stackOutput")
-        cpath = os.path.join(out_dir, f"{stem}_ContoursPM_{suffix}.tif")
-        tiffio.imsave(cpath, page(class_order[1]), append=False)
-        tiffio.imsave(cpath, preview, append=True)
-        tiffio.imsave(os.path.join(out_dir, f"{stem}_NucleiPM_{suffix}.tif"), page(class_order[2]), append=False)
+        plan = [(os.path.join(out_dir, f"{stem}_ContoursPM_{suffix}.tif"), [class_order[1]]),
+                (os.path.join(out_dir, f"{stem}_NucleiPM_{suffix}.tif"), [class_order[2]])]
+    writers = []
+    for path, classes in plan:
+        w = tiffio.BigTiffWriter(path, append=False)
+        w.begin_pages(len(classes), H, W, np.uint8)
+        writers.append((w, classes))
+    bands: "queue.Queue" = queue.Queue(maxsize=4)
+    errors: List[BaseException] = []
+
+    def drain():
+        while True:
+            item = bands.get()
+            if item is None:
+                return
+            r0, _, buf = item
+            try:
+                for w, classes in writers:
+                    for i, cls in enumerate(classes):
+                        w.write_page_rows(i, r0, buf[cls])
+            except BaseException as ex:          # keep draining so the producer never blocks
+                errors.append(ex)
+
+    t = threading.Thread(target=drain)
+    t.start()
+    try:
+        for band in UNet2D.singleImageInferenceStream(image, premap=premap, infer_shape=infer_shape, cli_quant=True):
+            bands.put(band)
+    finally:
+        bands.put(None)
+        t.join()
+    if errors:
+        raise errors[0]
+    for w, _ in writers:
+        w.end_pages()
+    # the raw preview follows the contour page: qc/<stem>_Preview (stack mode) or <stem>_ContoursPM (UnMicst1-5.py:857-872)
+    if len(writers) > 1 or not args.stackOutput:
+        (writers[1][0] if args.stackOutput else writers[0][0]).write_page(preview)
+    for w, _ in writers:
+        w.close()
     return 0
 
 

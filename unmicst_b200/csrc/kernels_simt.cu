@@ -9,6 +9,11 @@
 //  gather_tiles       PI2D.getPatch + (patch-mean)/std (PartitionOfImage.py:77-82, UnMicst1-5.py:700)
 //  stitch_kernel      PI2D.patchOutput/getValidOutput as an atomic-free gather
 //                     (PartitionOfImage.py:92-122) + np.uint8(255*p) (UnMicst1-5.py:848)
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
 #include "umx_kernels.cuh"
 #include "../../include/unmicst_b200.h"
 
@@ -449,6 +454,87 @@ __device__ __forceinline__ double load_sample(const void* img, int dtype, int64_
     }
 }
 
+// ---- skimage.transform.resize semantics (see umx_kernels.cuh: Resample), float64, scipy's operation order:
+// no FMA contraction (__dmul_rn / __dadd_rn), bilinear terms summed (0,0), (0,1), (1,0), (1,1), each (v * wy) * wx.
+__device__ __forceinline__ int mirror_idx(int i, int n) {      // ndimage 'mirror': d c b | a b c d | c b a
+    if (n <= 1) return 0;
+    const int p = 2 * n - 2;
+    i = i < 0 ? -i : i;
+    if (i >= p) i %= p;
+    return i >= n ? p - i : i;
+}
+
+struct AxisTaps { int s0, s1; double t; };
+
+// output index k -> the two source samples and the weight of the second one (NI_ZoomShift with grid_mode: the
+// coordinate (k + 0.5) * zoom - 0.5 is reflected when negative; a right neighbour past the end mirrors to n - 2)
+__device__ __forceinline__ AxisTaps axis_taps(int k, double zoom, int n) {
+    double cc = __dsub_rn(__dmul_rn((double)k + 0.5, zoom), 0.5);
+    if (cc < 0.0) cc = -cc;
+    AxisTaps a;
+    a.s0 = (int)floor(cc);
+    if (a.s0 > n - 1) a.s0 = n - 1;
+    a.t = cc - (double)a.s0;
+    a.s1 = a.s0 + 1;
+    if (a.s1 >= n) a.s1 = n > 1 ? 2 * n - 2 - a.s1 : 0;
+    return a;
+}
+
+// Gaussian-filtered source sample at (r, c): axis 0 first, then axis 1 (ndimage.gaussian_filter), each pass in
+// correlate1d's symmetric form  x[0]*g[0] + sum_{j<0} (x[j] + x[-j]) * g[j].
+template <typename Fetch>
+__device__ __forceinline__ double filtered_sample(const Fetch& f, const Resample& rs, int r, int c) {
+    if (rs.ry == 0 && rs.rx == 0) return f(r, c);
+    auto column = [&](int cc) -> double {
+        if (rs.ry == 0) return f(r, cc);
+        double acc = __dmul_rn(f(r, cc), rs.gy[rs.ry]);
+        for (int j = -rs.ry; j < 0; ++j) {
+            const double pair = __dadd_rn(f(mirror_idx(r + j, rs.src_h), cc), f(mirror_idx(r - j, rs.src_h), cc));
+            acc = __dadd_rn(acc, __dmul_rn(pair, rs.gy[rs.ry + j]));
+        }
+        return acc;
+    };
+    if (rs.rx == 0) return column(c);
+    double acc = __dmul_rn(column(c), rs.gx[rs.rx]);
+    for (int j = -rs.rx; j < 0; ++j) {
+        const double pair = __dadd_rn(column(mirror_idx(c + j, rs.src_w)), column(mirror_idx(c - j, rs.src_w)));
+        acc = __dadd_rn(acc, __dmul_rn(pair, rs.gx[rs.rx + j]));
+    }
+    return acc;
+}
+
+template <typename Fetch>
+__device__ __forceinline__ double resample_value(const Fetch& f, const Resample& rs, int y, int x) {
+    const AxisTaps ay = axis_taps(y, rs.zoom_y, rs.src_h), ax = axis_taps(x, rs.zoom_x, rs.src_w);
+    const double wy0 = 1.0 - ay.t, wx0 = 1.0 - ax.t;
+    double v = __dmul_rn(__dmul_rn(filtered_sample(f, rs, ay.s0, ax.s0), wy0), wx0);
+    v = __dadd_rn(v, __dmul_rn(__dmul_rn(filtered_sample(f, rs, ay.s0, ax.s1), wy0), ax.t));
+    v = __dadd_rn(v, __dmul_rn(__dmul_rn(filtered_sample(f, rs, ay.s1, ax.s0), ay.t), wx0));
+    v = __dadd_rn(v, __dmul_rn(__dmul_rn(filtered_sample(f, rs, ay.s1, ax.s1), ay.t), ax.t));
+    return v;
+}
+
+__device__ __forceinline__ double rescale_sample(double v, const PreMap& pre) {      // rescale_intensity
+    v = fmin(fmax(v, pre.imin), pre.imax);
+    v = (v - pre.imin) / (pre.imax - pre.imin);
+    return v * (pre.omax - pre.omin) + pre.omin;
+}
+
+// every 8/16-bit sample code through the float64 map of the gather (entry n: the zero padding outside the image)
+__global__ void __launch_bounds__(256) norm_lut_kernel(const NormLutParams p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > p.n) return;
+    double v = 0.0;
+    if (i < p.n) {
+        v = (double)i;
+        if (p.has_pre) {
+            v = v * p.pre.in_scale;
+            if (p.pre.rescale) v = rescale_sample(v, p.pre);
+        }
+    }
+    p.out[i] = (float)((v - p.mean) / p.std_dev);
+}
+
 // out[t][y][x][c] = float((frame - mean)/std); frame = premap(sample) inside the image, 0 outside.
 __global__ void __launch_bounds__(256) gather_tiles_kernel(const GatherParams p) {
     const int64_t total = (int64_t)p.n_tiles * p.S * p.S;
@@ -463,21 +549,80 @@ __global__ void __launch_bounds__(256) gather_tiles_kernel(const GatherParams p)
     const int r = ti * p.sub + y - p.margin;     // image row
     const int c = tj * p.sub + x - p.margin;     // image col
     const bool inside = (r >= 0 && r < p.H && c >= 0 && c < p.W);
+    if (p.lut) {          // integer samples, no resampling: one table look-up replaces the float64 arithmetic bit for bit
+        const int n_codes = p.dtype == UMX_U8 ? 256 : 65536;
+        for (int ch = 0; ch < p.C; ++ch) {
+            int code = n_codes;
+            if (inside) {
+                const int64_t idx = (int64_t)((p.n_planes == 1) ? 0 : ch) * p.plane_stride + (int64_t)(r - p.img_row0) * p.W + c;
+                code = p.dtype == UMX_U8 ? (int)reinterpret_cast<const uint8_t*>(p.img)[idx] : (int)reinterpret_cast<const uint16_t*>(p.img)[idx];
+            }
+            p.out[i * p.C + ch] = __ldg(p.lut + ch * 65537 + code);
+        }
+        return;
+    }
     for (int ch = 0; ch < p.C; ++ch) {
         double v = 0.0;
         if (inside) {
             const int plane = (p.n_planes == 1) ? 0 : ch;
-            v = load_sample(p.img, p.dtype, (int64_t)plane * p.plane_stride + (int64_t)(r - p.img_row0) * p.W + c);
-            if (p.has_pre) {
-                v = v * p.pre.in_scale;
-                if (p.pre.rescale) {
-                    v = fmin(fmax(v, p.pre.imin), p.pre.imax);
-                    v = (v - p.pre.imin) / (p.pre.imax - p.pre.imin);
-                    v = v * (p.pre.omax - p.pre.omin) + p.pre.omin;
+            if (p.rs.on) {
+                const int64_t base = (int64_t)plane * p.plane_stride - (int64_t)p.img_row0 * p.rs.src_w;
+                const double sc = p.has_pre ? p.pre[ch].in_scale : 1.0;
+                auto fetch = [&](int rr, int cc) -> double {
+                    return __dmul_rn(load_sample(p.img, p.dtype, base + (int64_t)rr * p.rs.src_w + cc), sc);
+                };
+                v = resample_value(fetch, p.rs, r, c);
+                if (p.has_pre && p.pre[ch].rescale) v = rescale_sample(v, p.pre[ch]);
+            } else {
+                v = load_sample(p.img, p.dtype, (int64_t)plane * p.plane_stride + (int64_t)(r - p.img_row0) * p.W + c);
+                if (p.has_pre) {
+                    v = v * p.pre[ch].in_scale;
+                    if (p.pre[ch].rescale) v = rescale_sample(v, p.pre[ch]);
                 }
             }
         }
         p.out[i * p.C + ch] = (float)((v - p.mean) / p.std_dev);
+    }
+}
+
+// One thread per destination pixel, all K planes: uint8 page * (1/255) -> resize -> np.uint8(255 * x).
+__global__ void __launch_bounds__(256) resize_u8_kernel(const ResizeU8Params p) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = p.row0 + blockIdx.y;
+    if (x >= p.dst_w || y >= p.row1) return;
+    for (int k = 0; k < p.K; ++k) {
+        const uint8_t* plane = p.src + (int64_t)k * p.src_plane_stride - (int64_t)p.src_row0 * p.rs.src_w;
+        auto fetch = [&](int rr, int cc) -> double {
+            return __dmul_rn((double)__ldg(plane + (int64_t)rr * p.rs.src_w + cc), 1.0 / 255);
+        };
+        const double v = resample_value(fetch, p.rs, y, x);
+        p.out[(int64_t)k * p.out_plane_stride + (int64_t)(y - p.out_row_base) * p.dst_w + x] = (uint8_t)fmin(255.0, fmax(0.0, floor(__dmul_rn(255.0, v))));
+    }
+}
+
+__device__ __forceinline__ unsigned long long minmax_encode(double v) {      // order-preserving double -> uint64
+    const long long b = __double_as_longlong(v);
+    return b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull);
+}
+
+__global__ void __launch_bounds__(256) resample_minmax_kernel(const MinMaxParams p) {
+    const int64_t total = (int64_t)p.dst_h * p.dst_w;
+    double lo = INFINITY, hi = -INFINITY;
+    auto fetch = [&](int rr, int cc) -> double {
+        return __dmul_rn(load_sample(p.img, p.dtype, (int64_t)rr * p.rs.src_w + cc), p.in_scale);
+    };
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int y = (int)(i / p.dst_w), x = (int)(i % p.dst_w);
+        const double v = p.rs.on ? resample_value(fetch, p.rs, y, x) : fetch(y, x);
+        lo = fmin(lo, v); hi = fmax(hi, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0 && lo <= hi) {
+        atomicMin(p.out + 0, minmax_encode(lo));
+        atomicMax(p.out + 1, minmax_encode(hi));
     }
 }
 
@@ -500,6 +645,12 @@ __global__ void __launch_bounds__(256) stitch_kernel(const StitchParams p) {
 #pragma unroll
     for (int k = 0; k < K; ++k) num[k] = 0.f;
     float cnt = 0.f;
+    if (p.replace) {        // tiles are patched in row-major order: the lower-right tile covering the pixel is the last writer
+        const float* q = p.probs + ((((int64_t)(ti1 - p.tr_lo) * p.npc + tj1) * p.S + (R - ti1 * p.sub)) * p.S + (Cc - tj1 * p.sub)) * K;
+#pragma unroll
+        for (int k = 0; k < K; ++k) num[k] = __ldg(q + k);
+        cnt = 1.f;
+    } else
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
         const int ti = ti1 - a;
@@ -527,7 +678,11 @@ __global__ void __launch_bounds__(256) stitch_kernel(const StitchParams p) {
     for (int k = 0; k < K; ++k) {
         const float v = num[k] / cnt;
         if (p.out_f32) p.out_f32[k * p.out_plane_stride + o] = v;
-        if (p.out_u8) p.out_u8[k * p.out_plane_stride + o] = (uint8_t)fminf(255.f, floorf(255.f * v));
+        if (p.out_u8) {
+            uint8_t q = (uint8_t)fminf(255.f, floorf(255.f * v));
+            if (p.requant) q = (uint8_t)(__dmul_rn(255.0, __dmul_rn((double)q, 1.0 / 255)));      // second quantisation at equal size
+            p.out_u8[k * p.out_plane_stride + o] = q;
+        }
     }
 }
 
@@ -609,6 +764,60 @@ cudaError_t launch_gather_tiles(const GatherParams& p, cudaStream_t s) {
     if (total == 0) return cudaSuccess;
     gather_tiles_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p);
     return cudaGetLastError();
+}
+
+cudaError_t launch_norm_lut(const NormLutParams& p, cudaStream_t s) {
+    norm_lut_kernel<<<(p.n + 1 + 255) / 256, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_resize_u8(const ResizeU8Params& p, cudaStream_t s) {
+    if (p.row1 <= p.row0) return cudaSuccess;
+    dim3 grid((p.dst_w + 255) / 256, p.row1 - p.row0);
+    resize_u8_kernel<<<grid, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_resample_minmax(const MinMaxParams& p, cudaStream_t s) {
+    const int64_t total = (int64_t)p.dst_h * p.dst_w;
+    if (total == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, 148 * 16);
+    resample_minmax_kernel<<<blocks, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+double minmax_decode(unsigned long long code) {
+    const unsigned long long b = (code & 0x8000000000000000ull) ? (code & 0x7FFFFFFFFFFFFFFFull) : ~code;
+    double v;
+    memcpy(&v, &b, sizeof v);
+    return v;
+}
+
+// ndimage's Gaussian taps: radius int(4 sigma + 0.5), exp(-0.5 x^2 / sigma^2) normalised to sum 1
+static int gaussian_taps(double sigma, double* g) {
+    if (!(sigma > 1e-15)) return 0;
+    const int r = (int)(4.0 * sigma + 0.5);
+    if (r > kMaxResampleRadius) return -1;
+    double sum = 0.0;
+    for (int i = -r; i <= r; ++i) { g[i + r] = exp(-0.5 / (sigma * sigma) * (double)(i * i)); sum += g[i + r]; }
+    for (int i = 0; i <= 2 * r; ++i) g[i] /= sum;
+    return r;
+}
+
+bool make_resample(Resample* rs, int src_h, int src_w, int dst_h, int dst_w) {
+    memset(rs, 0, sizeof(*rs));
+    rs->src_h = src_h; rs->src_w = src_w;
+    if (src_h == dst_h && src_w == dst_w) return true;
+    rs->on = 1;
+    rs->zoom_y = (double)src_h / (double)dst_h; rs->zoom_x = (double)src_w / (double)dst_w;
+    // anti-aliasing whenever some axis shrinks, sigma = max(0, (factor - 1) / 2) per axis (skimage defaults)
+    if (dst_h < src_h || dst_w < src_w) {
+        const int ry = gaussian_taps(std::max(0.0, (rs->zoom_y - 1.0) / 2.0), rs->gy);
+        const int rx = gaussian_taps(std::max(0.0, (rs->zoom_x - 1.0) / 2.0), rs->gx);
+        if (ry < 0 || rx < 0) return false;
+        rs->ry = ry; rs->rx = rx;
+    }
+    return true;
 }
 
 cudaError_t launch_stitch(const StitchParams& p, cudaStream_t s) {

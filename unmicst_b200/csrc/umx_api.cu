@@ -1011,6 +1011,10 @@ void umx_destroy(umx_handle* h) {
     for (auto& b : h->bufs) { if (b.d) cudaFree(b.d); if (b.dh) cudaFree(b.dh); }
     if (h->probs) cudaFree(h->probs);
     if (h->d_dbg) cudaFree(h->d_dbg);
+    if (h->d_band_u8) cudaFree(h->d_band_u8);
+    if (h->d_out_u8) cudaFree(h->d_out_u8);
+    if (h->d_lut) cudaFree(h->d_lut);
+    if (h->d_minmax) cudaFree(h->d_minmax);
     if (h->d_img) cudaFree(h->d_img);
     if (h->d_probs_rows) cudaFree(h->d_probs_rows);
     for (int i = 0; i < 2; ++i) {
@@ -1082,8 +1086,11 @@ int64_t umx_debug_buffer(umx_handle* h, const char* name, int32_t n_tiles, float
 }
 
 int umx_forward_tiles(umx_handle* h, const float* tiles, int32_t n_tiles, float* probs, int32_t precision) {
-    (void)precision;
     if (!h || n_tiles < 0 || (n_tiles > 0 && (!tiles || !probs))) { set_error("umx_forward_tiles: bad argument"); return UMX_EINVAL; }
+    if (precision != UMX_PREC_DEFAULT && precision != h->precision) {
+        set_error("umx_forward_tiles: precision %d requested but the handle was built with %d (the arithmetic is fixed at umx_create)", precision, h->precision);
+        return UMX_EINVAL;
+    }
     UMX_CUDA_TRY(cudaSetDevice(h->device));
     const size_t in_tile = (size_t)h->S * h->S * h->C, out_tile = (size_t)h->S * h->S * h->K;
     for (int t0 = 0; t0 < n_tiles; t0 += h->max_batch) {
@@ -1112,6 +1119,82 @@ int umx_band_rows(umx_handle* h, int32_t H, int32_t tr0, int32_t tr1, int32_t* r
     return UMX_OK;
 }
 
+}  // extern "C"
+
+namespace umx {
+namespace {
+
+// first / last source row the resize of destination row y touches (before mirroring, which only acts at the borders)
+void resize_window(const Resample& rs, int y, int* lo, int* hi) {
+    if (!rs.on) { *lo = *hi = y; return; }
+    double cc = ((double)y + 0.5) * rs.zoom_y - 0.5;
+    if (cc < 0) cc = -cc;
+    const int s0 = (int)floor(cc);
+    *lo = s0 - rs.ry; *hi = s0 + 1 + rs.ry;
+}
+
+// Raw-grid rows a tile-row band owns when its pages are resized back (see umx_band_out_rows): the cut between two
+// bands is the first raw row whose window reaches the inference rows the upper band does not emit.
+int raw_cut(const umx_handle* h, const Resample& rs_out, int infer_h, int raw_h, int t) {
+    const int npr = (infer_h + h->sub - 1) / h->sub;
+    if (t <= 0) return 0;
+    if (t >= npr) return raw_h;
+    const int bound = t * h->sub - h->margin;          // first inference row the bands above do not emit
+    int y = std::max(0, (int)floor((bound - 2 - rs_out.ry) / std::max(rs_out.zoom_y, 1e-9)) - 2);
+    for (; y < raw_h; ++y) {
+        int lo, hi; resize_window(rs_out, y, &lo, &hi);
+        if (hi >= bound) break;
+    }
+    return std::min(y, raw_h);
+}
+
+}  // namespace
+}  // namespace umx
+
+extern "C" {
+
+int umx_band_out_rows(umx_handle* h, int32_t infer_h, int32_t tr0, int32_t tr1, int32_t raw_h, int32_t* row0, int32_t* row1) {
+    if (!h || infer_h <= 0 || raw_h <= 0) { set_error("umx_band_out_rows: bad argument"); return UMX_EINVAL; }
+    if (raw_h == infer_h) return umx_band_rows(h, infer_h, tr0, tr1, row0, row1);
+    const int npr = (infer_h + h->sub - 1) / h->sub;
+    if (tr1 <= 0 || tr1 > npr) tr1 = npr;
+    if (tr0 < 0 || tr0 >= tr1) { set_error("umx_band_out_rows: empty band"); return UMX_EINVAL; }
+    Resample rs;
+    if (!make_resample(&rs, infer_h, 1, raw_h, 1)) { set_error("scaling factor too large for the resize kernel"); return UMX_EINVAL; }
+    if (row0) *row0 = raw_cut(h, rs, infer_h, raw_h, tr0);
+    if (row1) *row1 = raw_cut(h, rs, infer_h, raw_h, tr1);
+    return UMX_OK;
+}
+
+int umx_resample_minmax(umx_handle* h, const void* plane, int32_t dtype, int32_t H, int32_t W, int32_t out_h, int32_t out_w,
+                        double in_scale, double* min_out, double* max_out) {
+    if (!h || !plane || H <= 0 || W <= 0 || out_h <= 0 || out_w <= 0 || dtype_size(dtype) == 0) { set_error("umx_resample_minmax: bad argument"); return UMX_EINVAL; }
+    UMX_CUDA_TRY(cudaSetDevice(h->device));
+    MinMaxParams mp{};
+    if (!make_resample(&mp.rs, H, W, out_h, out_w)) { set_error("scaling factor too small for the resize kernel (Gaussian radius > %d)", kMaxResampleRadius); return UMX_EINVAL; }
+    const size_t bytes = (size_t)H * W * dtype_size(dtype);
+    const void* src = plane;
+    if (!is_device_ptr(plane)) {
+        void* p = h->d_img;
+        UMX_TRY(ensure(&p, &h->d_img_bytes, bytes));
+        h->d_img = p;
+        UMX_CUDA_TRY(cudaMemcpyAsync(h->d_img, plane, bytes, cudaMemcpyHostToDevice, h->stream));
+        src = h->d_img;
+    }
+    if (!h->d_minmax) UMX_CUDA_TRY(cudaMalloc(&h->d_minmax, 2 * sizeof(unsigned long long)));
+    const unsigned long long init[2] = {~0ull, 0ull};
+    UMX_CUDA_TRY(cudaMemcpyAsync(h->d_minmax, init, sizeof init, cudaMemcpyHostToDevice, h->stream));
+    mp.img = src; mp.dtype = dtype; mp.dst_h = out_h; mp.dst_w = out_w; mp.in_scale = in_scale; mp.out = h->d_minmax;
+    UMX_CUDA_TRY(launch_resample_minmax(mp, h->stream));
+    h->launches += 1;
+    unsigned long long res[2];
+    UMX_CUDA_TRY(cudaMemcpyAsync(res, h->d_minmax, sizeof res, cudaMemcpyDeviceToHost, h->stream));
+    UMX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (min_out) *min_out = minmax_decode(res[0]);
+    if (max_out) *max_out = minmax_decode(res[1]);
+    return UMX_OK;
+}
+
 int umx_infer_image(umx_handle* h, const void* img, int32_t dtype, int32_t n_planes, int32_t H, int32_t W,
                     int64_t plane_stride, double mean, double std_dev, uint8_t* out_u8, float* out_f32,
                     const umx_opts* opts) {
@@ -1119,43 +1202,88 @@ int umx_infer_image(umx_handle* h, const void* img, int32_t dtype, int32_t n_pla
     if (n_planes != 1 && n_planes != h->C) { set_error("image has %d planes, network takes %d channels", n_planes, h->C); return UMX_EINVAL; }
     if (!out_u8 && !out_f32) { set_error("umx_infer_image: no output requested"); return UMX_EINVAL; }
     if (std_dev == 0.0) { set_error("std is zero"); return UMX_EINVAL; }
+    if (opts && opts->precision != UMX_PREC_DEFAULT && opts->precision != h->precision) {
+        set_error("umx_infer_image: precision %d requested but the handle was built with %d (the arithmetic is fixed at umx_create)", opts->precision, h->precision);
+        return UMX_EINVAL;
+    }
     UMX_CUDA_TRY(cudaSetDevice(h->device));
+    // RH x RW: the samples in img; IH x IW: the grid the network runs on (a resized view when --scalingFactor != 1)
+    const int RH = H, RW = W;
+    const int IH = (opts && opts->infer_h > 0) ? opts->infer_h : RH, IW = (opts && opts->infer_w > 0) ? opts->infer_w : RW;
+    const bool cli_quant = opts && (opts->flags & UMX_F_CLI_QUANT);
+    Resample rs_in, rs_out;
+    if (!make_resample(&rs_in, RH, RW, IH, IW) || !make_resample(&rs_out, IH, IW, RH, RW)) {
+        set_error("scaling %dx%d -> %dx%d needs a Gaussian radius > %d", RH, RW, IH, IW, kMaxResampleRadius); return UMX_EINVAL;
+    }
+    const bool resize_back = cli_quant && rs_in.on;
+    if (cli_quant && (!out_u8 || out_f32)) { set_error("UMX_F_CLI_QUANT produces out_u8 only"); return UMX_EINVAL; }
     const int S = h->S, m = h->margin, sub = h->sub, K = h->K;
-    const int npr = (H + sub - 1) / sub, npc = (W + sub - 1) / sub;
+    const int npr = (IH + sub - 1) / sub, npc = (IW + sub - 1) / sub;
     const int frame_rows = npr * sub + 2 * m;
     int ta = opts ? opts->tile_row0 : 0, tb = opts ? opts->tile_row1 : 0;
     if (tb <= 0 || tb > npr) tb = npr;
     if (ta < 0 || ta >= tb) { set_error("empty tile-row band [%d,%d) of %d", ta, tb, npr); return UMX_EINVAL; }
-    if (plane_stride == 0) plane_stride = (int64_t)H * W;
-    int64_t out_ps = (opts && opts->out_plane_stride) ? opts->out_plane_stride : (int64_t)H * W;
+    if (plane_stride == 0) plane_stride = (int64_t)RH * RW;
+    const int64_t out_grid = resize_back ? (int64_t)RH * RW : (int64_t)IH * IW;
+    int64_t out_ps = (opts && opts->out_plane_stride) ? opts->out_plane_stride : out_grid;
     const int out_row_base = opts ? opts->out_row_base : 0;
-    const int t_first = std::max(ta - 1, 0);
+    // UMX_F_CONTINUE: the tile row above the seam was left in slot 0 of d_probs_rows by the previous call
+    const bool cont = opts && (opts->flags & UMX_F_CONTINUE) && ta > 0 && h->carry_row == ta - 1 && h->carry_h == IH && h->carry_w == IW &&
+                      h->d_probs_rows != nullptr;
+    const int t_first = cont ? ta : std::max(ta - 1, 0);
     const size_t esz = dtype_size(dtype);
 
-    // ---- image rows this band touches
-    const int ir0 = std::max(0, t_first * sub - m), ir1 = std::min(H, (tb - 1) * sub + S - m);
+    // ---- rows of the network grid this band reads, and the source rows behind them
+    const int ir0 = std::max(0, t_first * sub - m), ir1 = std::min(IH, (tb - 1) * sub + S - m);
+    int sr0 = ir0, sr1 = ir1;
+    if (rs_in.on) {
+        int lo, hi, lo2, hi2;
+        resize_window(rs_in, ir0, &lo, &hi); resize_window(rs_in, std::max(ir0, ir1 - 1), &lo2, &hi2);
+        sr0 = std::max(0, std::min(lo, lo2) - 1); sr1 = std::min(RH, std::max(hi, hi2) + 2);
+        if (ir0 == 0) sr0 = 0;
+        if (ir1 == IH) sr1 = RH;
+        // mirrored taps near the image borders stay within the rows just selected (they reflect into [0, 2R])
+        sr1 = std::max(sr1, std::min(RH, 2 * (rs_in.ry + 2))); if (sr0 > 0 && sr0 < 2 * (rs_in.ry + 2)) sr0 = 0;
+        if (RH - sr1 < 2 * (rs_in.ry + 2)) sr1 = RH;
+    }
     GatherParams gp{};
-    gp.dtype = dtype; gp.n_planes = n_planes; gp.H = H; gp.W = W; gp.S = S; gp.margin = m; gp.sub = sub; gp.npc = npc;
-    gp.C = h->C; gp.mean = mean; gp.std_dev = std_dev;
+    gp.dtype = dtype; gp.n_planes = n_planes; gp.H = IH; gp.W = IW; gp.S = S; gp.margin = m; gp.sub = sub; gp.npc = npc;
+    gp.C = h->C; gp.mean = mean; gp.std_dev = std_dev; gp.rs = rs_in;
+    if (h->C > kMaxImagePlanes) { set_error("networks with more than %d input channels are not supported by the tiling driver", kMaxImagePlanes); return UMX_EINVAL; }
     if (opts && opts->premap) {
         gp.has_pre = 1;
-        gp.pre.in_scale = opts->premap->in_scale; gp.pre.rescale = opts->premap->rescale;
-        gp.pre.imin = opts->premap->imin; gp.pre.imax = opts->premap->imax;
-        gp.pre.omin = opts->premap->omin; gp.pre.omax = opts->premap->omax;
+        const bool per_plane = (opts->flags & UMX_F_PREMAP_PER_PLANE) != 0;
+        for (int c = 0; c < h->C; ++c) {
+            const umx_premap& pm = opts->premap[per_plane ? c : 0];
+            gp.pre[c].in_scale = pm.in_scale; gp.pre[c].rescale = pm.rescale;
+            gp.pre[c].imin = pm.imin; gp.pre[c].imax = pm.imax; gp.pre[c].omin = pm.omin; gp.pre[c].omax = pm.omax;
+        }
     }
     if (is_device_ptr(img)) {
-        gp.img = img; gp.plane_stride = plane_stride; gp.img_row0 = 0; gp.img_rows = H;
+        gp.img = img; gp.plane_stride = plane_stride; gp.img_row0 = 0; gp.img_rows = RH;
     } else {
-        const int nrows = ir1 - ir0;
+        const int nrows = sr1 - sr0;
         void* p = h->d_img;
-        UMX_TRY(ensure(&p, &h->d_img_bytes, (size_t)n_planes * nrows * W * esz));
+        UMX_TRY(ensure(&p, &h->d_img_bytes, (size_t)n_planes * nrows * RW * esz));
         h->d_img = p;
         for (int pl = 0; pl < n_planes; ++pl) {
-            const char* src = (const char*)img + ((size_t)pl * plane_stride + (size_t)ir0 * W) * esz;
-            char* dst = (char*)h->d_img + (size_t)pl * nrows * W * esz;
-            UMX_CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)nrows * W * esz, cudaMemcpyHostToDevice, h->stream));
+            const char* src = (const char*)img + ((size_t)pl * plane_stride + (size_t)sr0 * RW) * esz;
+            char* dst = (char*)h->d_img + (size_t)pl * nrows * RW * esz;
+            UMX_CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)nrows * RW * esz, cudaMemcpyHostToDevice, h->stream));
         }
-        gp.img = h->d_img; gp.plane_stride = (int64_t)nrows * W; gp.img_row0 = ir0; gp.img_rows = nrows;
+        gp.img = h->d_img; gp.plane_stride = (int64_t)nrows * RW; gp.img_row0 = sr0; gp.img_rows = nrows;
+    }
+    // integer samples at native size: the float64 normalisation of every possible code once, then one look-up per pixel
+    if (!rs_in.on && (dtype == UMX_U8 || dtype == UMX_U16)) {
+        if (!h->d_lut) UMX_CUDA_TRY(cudaMalloc(&h->d_lut, (size_t)kMaxImagePlanes * 65537 * sizeof(float)));
+        for (int c = 0; c < h->C; ++c) {
+            NormLutParams lp{};
+            lp.n = dtype == UMX_U8 ? 256 : 65536; lp.mean = mean; lp.std_dev = std_dev; lp.pre = gp.pre[c]; lp.has_pre = gp.has_pre;
+            lp.out = h->d_lut + (size_t)c * 65537;
+            UMX_CUDA_TRY(launch_norm_lut(lp, h->stream));
+            h->launches += 1;
+        }
+        gp.lut = h->d_lut;
     }
 
     // ---- tile-row groups; probs of a group (+ the carried previous tile row) stay on the device
@@ -1164,27 +1292,47 @@ int umx_infer_image(umx_handle* h, const void* img, int32_t dtype, int32_t n_pla
     {
         void* p = h->d_probs_rows;
         UMX_TRY(ensure(&p, &h->d_probs_rows_bytes, (size_t)(rpg + 1) * row_elems * sizeof(float)));
+        if (p != h->d_probs_rows && cont) { set_error("UMX_F_CONTINUE: the workspace changed size between the calls"); h->d_probs_rows = (float*)p; h->carry_row = -1; return UMX_EINVAL; }
         h->d_probs_rows = (float*)p;
+    }
+    h->carry_row = -1;
+    if (out_u8 && out_f32 && is_device_ptr(out_u8) != is_device_ptr(out_f32)) {
+        set_error("out_u8 and out_f32 must both be host or both be device pointers"); return UMX_EINVAL;
     }
     const bool u8_direct = out_u8 && is_device_ptr(out_u8);
     const bool f32_direct = out_f32 && is_device_ptr(out_f32);
     const int max_rows = rpg * sub + 2 * m;
-    if (out_u8 && !u8_direct && h->d_stage_u8_bytes < (size_t)K * max_rows * W) {
-        for (int i = 0; i < 2; ++i) { if (h->d_stage_u8[i]) cudaFree(h->d_stage_u8[i]); h->d_stage_u8[i] = nullptr; }
-        for (int i = 0; i < 2; ++i) UMX_CUDA_TRY(cudaMalloc(&h->d_stage_u8[i], (size_t)K * max_rows * W));
-        h->d_stage_u8_bytes = (size_t)K * max_rows * W;
-    }
-    if (out_f32 && !f32_direct && h->d_stage_f32_bytes < (size_t)K * max_rows * W * 4) {
-        for (int i = 0; i < 2; ++i) { if (h->d_stage_f32[i]) cudaFree(h->d_stage_f32[i]); h->d_stage_f32[i] = nullptr; }
-        for (int i = 0; i < 2; ++i) UMX_CUDA_TRY(cudaMalloc(&h->d_stage_f32[i], (size_t)K * max_rows * W * 4));
-        h->d_stage_f32_bytes = (size_t)K * max_rows * W * 4;
+    // resize_back: the band's maps stay on the device at the network's size, rows [E0, E1): everything the tile rows
+    // t_first .. tb-1 complete (the seam tile row is recomputed anyway, so the rows above the band's own come for free
+    // and give the resize window its upper halo); the pages are resized in one pass after the last group.
+    const int E0 = (resize_back && ta > 0) ? std::min(IH, (ta - 1) * sub + m) : 0;
+    const int E1 = std::min(IH, std::max(0, ((tb == npr) ? frame_rows : tb * sub) - m));
+    int Y0 = 0, Y1 = 0;
+    if (resize_back) {
+        Y0 = raw_cut(h, rs_out, IH, RH, ta); Y1 = raw_cut(h, rs_out, IH, RH, tb);
+        int lo, hi; resize_window(rs_out, Y0, &lo, &hi);
+        if (ta > 0 && lo < E0) { set_error("scaling factor too extreme for banded output (resize window exceeds the seam tile row)"); return UMX_EINVAL; }
+        void* p = h->d_band_u8;
+        UMX_TRY(ensure(&p, &h->d_band_u8_bytes, (size_t)K * (E1 - E0) * IW));
+        h->d_band_u8 = (uint8_t*)p;
+    } else {
+        if (out_u8 && !u8_direct && h->d_stage_u8_bytes < (size_t)K * max_rows * IW) {
+            for (int i = 0; i < 2; ++i) { if (h->d_stage_u8[i]) cudaFree(h->d_stage_u8[i]); h->d_stage_u8[i] = nullptr; }
+            for (int i = 0; i < 2; ++i) UMX_CUDA_TRY(cudaMalloc(&h->d_stage_u8[i], (size_t)K * max_rows * IW));
+            h->d_stage_u8_bytes = (size_t)K * max_rows * IW;
+        }
+        if (out_f32 && !f32_direct && h->d_stage_f32_bytes < (size_t)K * max_rows * IW * 4) {
+            for (int i = 0; i < 2; ++i) { if (h->d_stage_f32[i]) cudaFree(h->d_stage_f32[i]); h->d_stage_f32[i] = nullptr; }
+            for (int i = 0; i < 2; ++i) UMX_CUDA_TRY(cudaMalloc(&h->d_stage_f32[i], (size_t)K * max_rows * IW * 4));
+            h->d_stage_f32_bytes = (size_t)K * max_rows * IW * 4;
+        }
     }
     const int s_gather = aux_slot(h, "gather_tiles"), s_stitch = aux_slot(h, "stitch_quantize");
     int gi = 0;
     bool copies_pending[2] = {false, false};
     for (int g0 = t_first; g0 < tb; g0 += rpg, ++gi) {
         const int g1 = std::min(g0 + rpg, tb);
-        const int lo = (g0 > t_first) ? g0 - 1 : g0;            // first tile row held in d_probs_rows
+        const int lo = (g0 > t_first || cont) ? g0 - 1 : g0;    // first tile row held in d_probs_rows
         float* group_base = h->d_probs_rows + (size_t)(g0 - lo) * row_elems;
         const int tile_begin = g0 * npc, tile_end = g1 * npc;
         for (int t0 = tile_begin; t0 < tile_end; t0 += h->max_batch) {
@@ -1198,53 +1346,79 @@ int umx_infer_image(umx_handle* h, const void* img, int32_t dtype, int32_t n_pla
             UMX_TRY(run_network(h, nb, group_base + (size_t)(t0 - tile_begin) * S * S * K));
         }
         // ---- emit the padded-frame rows this group completes
-        const int p0 = std::max(g0, ta) * sub, p1 = (g1 == npr) ? frame_rows : g1 * sub;
-        const int r0 = std::min(H, std::max(0, p0 - m)), r1 = std::min(H, std::max(0, p1 - m));
+        int p0 = std::max(g0, ta) * sub;
+        if (resize_back && g0 == t_first && ta > 0) p0 = (ta - 1) * sub + 2 * m;       // the halo rows above the band (tile row ta-1 is in slot 0 or recomputed)
+        const int p1 = (g1 == npr) ? frame_rows : g1 * sub;
+        const int r0 = std::min(IH, std::max(0, p0 - m)), r1 = std::min(IH, std::max(0, p1 - m));
         if (r1 > r0) {
             const int sb = gi & 1;
             if (copies_pending[sb]) { UMX_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_copy[sb], 0)); copies_pending[sb] = false; }
             StitchParams sp{};
             sp.probs = h->d_probs_rows; sp.tr_lo = lo; sp.tr_hi = g1;
-            sp.S = S; sp.margin = m; sp.sub = sub; sp.npc = npc; sp.npr = npr; sp.K = K; sp.H = H; sp.W = W;
+            sp.S = S; sp.margin = m; sp.sub = sub; sp.npc = npc; sp.npr = npr; sp.K = K; sp.H = IH; sp.W = IW;
             sp.row0 = r0; sp.row1 = r1;
-            if (out_u8 && out_f32 && u8_direct != f32_direct) {
-                set_error("out_u8 and out_f32 must both be host or both be device pointers"); return UMX_EINVAL;
-            }
-            const bool staged = out_u8 ? !u8_direct : !f32_direct;
-            if (staged) {
+            sp.requant = (cli_quant && !resize_back) ? 1 : 0;
+            sp.replace = (opts && (opts->flags & UMX_F_STITCH_REPLACE)) ? 1 : 0;
+            const bool staged = !resize_back && (out_u8 ? !u8_direct : !f32_direct);
+            if (resize_back) {
+                sp.out_u8 = h->d_band_u8; sp.out_plane_stride = (int64_t)(E1 - E0) * IW; sp.out_row_base = E0;
+            } else if (staged) {
                 sp.out_u8 = out_u8 ? h->d_stage_u8[sb] : nullptr;
                 sp.out_f32 = out_f32 ? h->d_stage_f32[sb] : nullptr;
-                sp.out_plane_stride = (int64_t)max_rows * W; sp.out_row_base = r0;
+                sp.out_plane_stride = (int64_t)max_rows * IW; sp.out_row_base = r0;
             } else {
                 sp.out_u8 = out_u8; sp.out_f32 = out_f32; sp.out_plane_stride = out_ps; sp.out_row_base = out_row_base;
             }
             {
-                ScopedTimer tm(h, s_stitch, 0, (double)(r1 - r0) * W * K * (4.0 * 1.78 + (out_u8 ? 1 : 0) + (out_f32 ? 4 : 0)));
+                ScopedTimer tm(h, s_stitch, 0, (double)(r1 - r0) * IW * K * (4.0 * 1.78 + (out_u8 ? 1 : 0) + (out_f32 ? 4 : 0)));
                 UMX_CUDA_TRY(launch_stitch(sp, h->stream));
                 h->launches += 1;
             }
             if (staged) {
                 UMX_CUDA_TRY(cudaEventRecord(h->ev_stitch[sb], h->stream));
                 UMX_CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_stitch[sb], 0));
-                const size_t n = (size_t)(r1 - r0) * W;
+                const size_t n = (size_t)(r1 - r0) * IW;
                 for (int k = 0; k < K; ++k) {
                     if (out_u8)
-                        UMX_CUDA_TRY(cudaMemcpyAsync(out_u8 + (size_t)k * out_ps + (size_t)(r0 - out_row_base) * W,
-                                                     h->d_stage_u8[sb] + (size_t)k * max_rows * W, n, cudaMemcpyDeviceToHost, h->copy_stream));
+                        UMX_CUDA_TRY(cudaMemcpyAsync(out_u8 + (size_t)k * out_ps + (size_t)(r0 - out_row_base) * IW,
+                                                     h->d_stage_u8[sb] + (size_t)k * max_rows * IW, n, cudaMemcpyDeviceToHost, h->copy_stream));
                     if (out_f32)
-                        UMX_CUDA_TRY(cudaMemcpyAsync(out_f32 + (size_t)k * out_ps + (size_t)(r0 - out_row_base) * W,
-                                                     h->d_stage_f32[sb] + (size_t)k * max_rows * W, n * 4, cudaMemcpyDeviceToHost, h->copy_stream));
+                        UMX_CUDA_TRY(cudaMemcpyAsync(out_f32 + (size_t)k * out_ps + (size_t)(r0 - out_row_base) * IW,
+                                                     h->d_stage_f32[sb] + (size_t)k * max_rows * IW, n * 4, cudaMemcpyDeviceToHost, h->copy_stream));
                 }
                 UMX_CUDA_TRY(cudaEventRecord(h->ev_copy[sb], h->copy_stream));
                 copies_pending[sb] = true;
             }
         }
-        // ---- carry the last tile row of this group into slot 0 for the next group
-        if (g1 < tb) {
+        // ---- carry the last tile row of this group into slot 0 for the next group (or the next UMX_F_CONTINUE call)
+        {
             const float* last = h->d_probs_rows + (size_t)(g1 - 1 - lo) * row_elems;
             if (last != h->d_probs_rows)
                 UMX_CUDA_TRY(cudaMemcpyAsync(h->d_probs_rows, last, row_elems * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
         }
+    }
+    h->carry_row = tb - 1; h->carry_h = IH; h->carry_w = IW;
+    if (resize_back && Y1 > Y0) {
+        // uint8 pages at the network's size -> resize to the raw grid -> second quantisation (UnMicst1-5.py:850-853)
+        ResizeU8Params rp{};
+        rp.src = h->d_band_u8; rp.src_plane_stride = (int64_t)(E1 - E0) * IW; rp.src_row0 = E0; rp.src_rows = E1 - E0;
+        rp.K = K; rp.dst_h = RH; rp.dst_w = RW; rp.row0 = Y0; rp.row1 = Y1; rp.rs = rs_out;
+        if (u8_direct) { rp.out = out_u8; rp.out_plane_stride = out_ps; rp.out_row_base = out_row_base; }
+        else {
+            void* p = h->d_out_u8;
+            UMX_TRY(ensure(&p, &h->d_out_u8_bytes, (size_t)K * (Y1 - Y0) * RW));
+            h->d_out_u8 = (uint8_t*)p;
+            rp.out = h->d_out_u8; rp.out_plane_stride = (int64_t)(Y1 - Y0) * RW; rp.out_row_base = Y0;
+        }
+        {
+            ScopedTimer tm(h, aux_slot(h, "resize_pages"), 0, (double)(Y1 - Y0) * RW * K * (1.0 + rs_out.zoom_y * rs_out.zoom_x));
+            UMX_CUDA_TRY(launch_resize_u8(rp, h->stream));
+            h->launches += 1;
+        }
+        if (!u8_direct)
+            for (int k = 0; k < K; ++k)
+                UMX_CUDA_TRY(cudaMemcpyAsync(out_u8 + (size_t)k * out_ps + (size_t)(Y0 - out_row_base) * RW,
+                                             h->d_out_u8 + (size_t)k * (Y1 - Y0) * RW, (size_t)(Y1 - Y0) * RW, cudaMemcpyDeviceToHost, h->stream));
     }
     // make the caller's stream wait for outstanding D2H copies, then (by default) the host too
     for (int sb = 0; sb < 2; ++sb)
@@ -1253,6 +1427,123 @@ int umx_infer_image(umx_handle* h, const void* img, int32_t dtype, int32_t n_pla
         UMX_CUDA_TRY(cudaStreamSynchronize(h->stream));
         drain_profile(h);
     }
+    return UMX_OK;
+}
+
+int umx_infer_images(umx_handle* h, const umx_image* images, int32_t n_images, double mean, double std_dev, int32_t flags) {
+    if (!h || n_images < 0 || (n_images > 0 && !images)) { set_error("umx_infer_images: bad argument"); return UMX_EINVAL; }
+    if (std_dev == 0.0) { set_error("std is zero"); return UMX_EINVAL; }
+    if (h->C > kMaxImagePlanes) { set_error("networks with more than %d input channels are not supported by the tiling driver", kMaxImagePlanes); return UMX_EINVAL; }
+    UMX_CUDA_TRY(cudaSetDevice(h->device));
+    const int S = h->S, m = h->margin, sub = h->sub, K = h->K;
+    std::vector<int> tiles(n_images);
+    for (int i = 0; i < n_images; ++i) {
+        const umx_image& im = images[i];
+        if (!im.img || im.H <= 0 || im.W <= 0 || dtype_size(im.dtype) == 0 || (!im.out_u8 && !im.out_f32)) { set_error("umx_infer_images: image %d malformed", i); return UMX_EINVAL; }
+        if (im.n_planes != 1 && im.n_planes != h->C) { set_error("image %d has %d planes, network takes %d channels", i, im.n_planes, h->C); return UMX_EINVAL; }
+        if ((flags & UMX_F_CLI_QUANT) && (!im.out_u8 || im.out_f32)) { set_error("UMX_F_CLI_QUANT produces out_u8 only"); return UMX_EINVAL; }
+        tiles[i] = ((im.H + sub - 1) / sub) * ((im.W + sub - 1) / sub);
+    }
+    const int s_gather = aux_slot(h, "gather_tiles"), s_stitch = aux_slot(h, "stitch_quantize");
+    h->carry_row = -1;
+    int i = 0;
+    while (i < n_images) {
+        if (tiles[i] > h->max_batch) {        // a large image: the tile-row-group driver
+            const umx_image& im = images[i];
+            umx_opts o{};
+            o.flags = flags & UMX_F_CLI_QUANT; o.premap = im.premap;
+            UMX_TRY(umx_infer_image(h, im.img, im.dtype, im.n_planes, im.H, im.W, im.plane_stride, mean, std_dev, im.out_u8, im.out_f32, &o));
+            ++i;
+            continue;
+        }
+        int j = i, total = 0;
+        size_t in_bytes = 0, u8_bytes = 0, f32_bytes = 0;
+        while (j < n_images && tiles[j] <= h->max_batch && total + tiles[j] <= h->max_batch) {
+            const umx_image& im = images[j];
+            total += tiles[j];
+            if (!is_device_ptr(im.img)) in_bytes += (((size_t)im.n_planes * im.H * im.W * dtype_size(im.dtype)) + 255) & ~(size_t)255;
+            if (im.out_u8 && !is_device_ptr(im.out_u8)) u8_bytes += (size_t)K * im.H * im.W;
+            if (im.out_f32 && !is_device_ptr(im.out_f32)) f32_bytes += (size_t)K * im.H * im.W * 4;
+            ++j;
+        }
+        {
+            void* p = h->d_img; UMX_TRY(ensure(&p, &h->d_img_bytes, std::max<size_t>(in_bytes, 256))); h->d_img = p;
+            p = h->d_out_u8; UMX_TRY(ensure(&p, &h->d_out_u8_bytes, std::max<size_t>(u8_bytes, 256))); h->d_out_u8 = (uint8_t*)p;
+            if (f32_bytes) {
+                if (h->d_stage_f32_bytes < f32_bytes) {
+                    for (int b = 0; b < 2; ++b) { if (h->d_stage_f32[b]) cudaFree(h->d_stage_f32[b]); h->d_stage_f32[b] = nullptr; }
+                    for (int b = 0; b < 2; ++b) UMX_CUDA_TRY(cudaMalloc(&h->d_stage_f32[b], f32_bytes));
+                    h->d_stage_f32_bytes = f32_bytes;
+                }
+            }
+        }
+        // ---- tiles of every image of the group into one launch batch
+        size_t in_off = 0;
+        int tile_off = 0;
+        for (int k = i; k < j; ++k) {
+            const umx_image& im = images[k];
+            const size_t esz = dtype_size(im.dtype);
+            const int64_t ps = im.plane_stride ? im.plane_stride : (int64_t)im.H * im.W;
+            GatherParams gp{};
+            gp.dtype = im.dtype; gp.n_planes = im.n_planes; gp.H = im.H; gp.W = im.W; gp.S = S; gp.margin = m; gp.sub = sub;
+            gp.npc = (im.W + sub - 1) / sub; gp.C = h->C; gp.mean = mean; gp.std_dev = std_dev;
+            make_resample(&gp.rs, im.H, im.W, im.H, im.W);
+            if (im.premap) {
+                gp.has_pre = 1;
+                for (int c = 0; c < h->C; ++c) {
+                    gp.pre[c].in_scale = im.premap->in_scale; gp.pre[c].rescale = im.premap->rescale; gp.pre[c].imin = im.premap->imin;
+                    gp.pre[c].imax = im.premap->imax; gp.pre[c].omin = im.premap->omin; gp.pre[c].omax = im.premap->omax;
+                }
+            }
+            if (is_device_ptr(im.img)) { gp.img = im.img; gp.plane_stride = ps; }
+            else {
+                char* dst = (char*)h->d_img + in_off;
+                for (int pl = 0; pl < im.n_planes; ++pl)
+                    UMX_CUDA_TRY(cudaMemcpyAsync(dst + (size_t)pl * im.H * im.W * esz, (const char*)im.img + (size_t)pl * ps * esz,
+                                                 (size_t)im.H * im.W * esz, cudaMemcpyHostToDevice, h->stream));
+                gp.img = dst; gp.plane_stride = (int64_t)im.H * im.W;
+                in_off += (((size_t)im.n_planes * im.H * im.W * esz) + 255) & ~(size_t)255;
+            }
+            gp.img_row0 = 0; gp.img_rows = im.H; gp.tile0 = 0; gp.n_tiles = tiles[k];
+            gp.out = h->bufs[h->in_buf].d + (size_t)tile_off * S * S * h->C;
+            {
+                ScopedTimer tm(h, s_gather, 0, (double)tiles[k] * S * S * (h->C * 4.0 + esz));
+                UMX_CUDA_TRY(launch_gather_tiles(gp, h->stream));
+                h->launches += 1;
+            }
+            tile_off += tiles[k];
+        }
+        UMX_TRY(run_network(h, total, h->probs));
+        // ---- stitch each image from its slice of the batch
+        tile_off = 0;
+        size_t u8_off = 0, f32_off = 0;
+        for (int k = i; k < j; ++k) {
+            const umx_image& im = images[k];
+            const int npr = (im.H + sub - 1) / sub, npc = (im.W + sub - 1) / sub;
+            const size_t n = (size_t)im.H * im.W;
+            StitchParams sp{};
+            sp.probs = h->probs + (size_t)tile_off * S * S * K; sp.tr_lo = 0; sp.tr_hi = npr;
+            sp.S = S; sp.margin = m; sp.sub = sub; sp.npc = npc; sp.npr = npr; sp.K = K; sp.H = im.H; sp.W = im.W;
+            sp.row0 = 0; sp.row1 = im.H; sp.out_plane_stride = (int64_t)n; sp.out_row_base = 0;
+            sp.requant = (flags & UMX_F_CLI_QUANT) ? 1 : 0;
+            const bool u8_dev = im.out_u8 && is_device_ptr(im.out_u8), f32_dev = im.out_f32 && is_device_ptr(im.out_f32);
+            sp.out_u8 = im.out_u8 ? (u8_dev ? im.out_u8 : h->d_out_u8 + u8_off) : nullptr;
+            sp.out_f32 = im.out_f32 ? (f32_dev ? im.out_f32 : (float*)((char*)h->d_stage_f32[0] + f32_off)) : nullptr;
+            {
+                ScopedTimer tm(h, s_stitch, 0, (double)n * K * (4.0 * 1.78 + (im.out_u8 ? 1 : 0) + (im.out_f32 ? 4 : 0)));
+                UMX_CUDA_TRY(launch_stitch(sp, h->stream));
+                h->launches += 1;
+            }
+            if (im.out_u8 && !u8_dev) { UMX_CUDA_TRY(cudaMemcpyAsync(im.out_u8, sp.out_u8, (size_t)K * n, cudaMemcpyDeviceToHost, h->stream)); u8_off += (size_t)K * n; }
+            if (im.out_f32 && !f32_dev) { UMX_CUDA_TRY(cudaMemcpyAsync(im.out_f32, sp.out_f32, (size_t)K * n * 4, cudaMemcpyDeviceToHost, h->stream)); f32_off += (size_t)K * n * 4; }
+            tile_off += tiles[k];
+        }
+        // the staging buffers are reused by the next group
+        UMX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        i = j;
+    }
+    UMX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    drain_profile(h);
     return UMX_OK;
 }
 

@@ -132,6 +132,11 @@ struct umx_handle {
     float* d_stage_f32[2] = {nullptr, nullptr}; size_t d_stage_f32_bytes = 0;
     cudaEvent_t ev_stitch[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    uint8_t* d_band_u8 = nullptr; size_t d_band_u8_bytes = 0;     // UMX_F_CLI_QUANT with resizing: the band's maps at inference size
+    uint8_t* d_out_u8 = nullptr; size_t d_out_u8_bytes = 0;       // ... and the resized pages before the D2H copy
+    int carry_row = -1; int carry_h = 0, carry_w = 0;             // tile row whose probabilities sit in slot 0 of d_probs_rows (UMX_F_CONTINUE)
+    float* d_lut = nullptr;                      // 65537-entry normalisation table for integer samples
+    unsigned long long* d_minmax = nullptr;      // umx_resample_minmax result
     unsigned long long* d_dbg = nullptr;         // UMX_TC_EXP=64 cycle counters
     // profiling
     bool profiling = false;

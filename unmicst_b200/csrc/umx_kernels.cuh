@@ -94,8 +94,21 @@ struct PreMap {                 // mirrors umx_premap
     double imin, imax, omin, omax;
 };
 
+// skimage.transform.resize(img, (dst_h, dst_w)) with its defaults (UnMicst1-5.py:813-815, :850), i.e.
+// scipy.ndimage.zoom(order=1, mode='mirror', grid_mode=True), preceded when an axis shrinks by
+// gaussian_filter(sigma=(in/out-1)/2, truncate=4, mode='mirror'); evaluated per output sample in float64.
+constexpr int kMaxResampleRadius = 16;
+constexpr int kMaxImagePlanes = 4;     // network input channels with their own PreMap / look-up table
+struct Resample {
+    int32_t on;                 // 0: identity (the source grid is the destination grid)
+    int32_t src_h, src_w;       // source grid
+    int32_t ry, rx;             // Gaussian radius per axis (0: no anti-aliasing on that axis)
+    double zoom_y, zoom_x;      // src / dst per axis (ndimage.zoom's coordinate scale with grid_mode=True)
+    double gy[2 * kMaxResampleRadius + 1], gx[2 * kMaxResampleRadius + 1];   // normalised Gaussian taps
+};
+
 struct GatherParams {           // PI2D.getPatch + (x-mean)/std for a run of tiles
-    const void* img;            // [C][img_rows][W] samples, device
+    const void* img;            // [C][img_rows][W] samples, device (the SOURCE grid when rs.on)
     int32_t dtype;              // UMX_U8/U16/F32/F64
     int32_t n_planes;           // planes present in img (1 may be broadcast to C)
     int64_t plane_stride;       // elements
@@ -106,9 +119,41 @@ struct GatherParams {           // PI2D.getPatch + (x-mean)/std for a run of til
     int32_t C;                  // network input channels
     int32_t tile0, n_tiles;     // global tile index of the first tile, count
     double mean, std_dev;
+    PreMap pre[kMaxImagePlanes]; // per network channel (the same map in every entry unless UMX_F_PREMAP_PER_PLANE)
+    int32_t has_pre;
+    Resample rs;                // rs.on: H x W is a resized view of the src_h x src_w samples in img (img_row0/img_rows/W-stride refer to the source)
+    const float* lut;           // optional: normalised value per 8/16-bit sample code (no resample): out = lut[ch * 65537 + sample]
+    float* out;                 // [n_tiles][S][S][C]
+};
+
+struct NormLutParams {          // builds GatherParams.lut: every possible 8/16-bit sample through the float64 map
+    int32_t n;                  // 256 or 65536
+    double mean, std_dev;
     PreMap pre;
     int32_t has_pre;
-    float* out;                 // [n_tiles][S][S][C]
+    float* out;
+};
+
+struct ResizeU8Params {         // uint8 page -> resize -> np.uint8(255 * x)   (UnMicst1-5.py:850-853), K planes
+    const uint8_t* src;         // [K][src_rows][src_w]: rows [src_row0, src_row0 + src_rows) of the source grid
+    int64_t src_plane_stride;
+    int32_t src_row0, src_rows;
+    int32_t K;
+    int32_t dst_h, dst_w;       // destination grid
+    int32_t row0, row1;         // destination rows to produce
+    Resample rs;                // src grid = the probability maps at inference size
+    uint8_t* out;               // [K][*][dst_w]; row r lands at r - out_row_base
+    int64_t out_plane_stride;
+    int32_t out_row_base;
+};
+
+struct MinMaxParams {           // min / max of img_as_float(img) resized to dst_h x dst_w (rescale_intensity's in_range)
+    const void* img;
+    int32_t dtype;
+    int32_t dst_h, dst_w;
+    double in_scale;
+    Resample rs;
+    unsigned long long* out;    // [2]: order-preserving encodings of min and max (see minmax_decode)
 };
 
 struct StitchParams {           // PI2D.patchOutput/getValidOutput as a gather + quantise
@@ -121,6 +166,8 @@ struct StitchParams {           // PI2D.patchOutput/getValidOutput as a gather +
     float*   out_f32;
     int64_t  out_plane_stride;  // elements between class planes
     int32_t  out_row_base;
+    int32_t  replace;           // 1: PI2D 'replace' mode (PartitionOfImage.py:99-100): the last tile written over a pixel wins, no weights
+    int32_t  requant;           // 1: out_u8 = uint8(255 * (uint8(255 p) * (1/255))), the reference's second quantisation at equal size (UnMicst1-5.py:850-853)
 };
 
 // launchers (kernels_simt.cu)
@@ -131,6 +178,12 @@ cudaError_t launch_taps(const TapsParams& p, cudaStream_t s);
 size_t first_conv_smem_bytes(int cin, int ks, int cout);
 cudaError_t launch_gather_tiles(const GatherParams& p, cudaStream_t s);
 cudaError_t launch_stitch(const StitchParams& p, cudaStream_t s);
+cudaError_t launch_norm_lut(const NormLutParams& p, cudaStream_t s);
+cudaError_t launch_resize_u8(const ResizeU8Params& p, cudaStream_t s);
+cudaError_t launch_resample_minmax(const MinMaxParams& p, cudaStream_t s);
+double minmax_decode(unsigned long long code);
+// host: fill a Resample for src -> dst (returns false when the Gaussian radius exceeds kMaxResampleRadius)
+bool make_resample(Resample* rs, int src_h, int src_w, int dst_h, int dst_w);
 cudaError_t conv_simt_configure();   // opt in to > 48 KB dynamic shared memory
 size_t conv_simt_smem_bytes(const ConvParams& p);
 

@@ -60,15 +60,25 @@ def tile_geometry(H: int, W: int, S: int) -> Tuple[int, int, int, int]:
     return m, sub, -(-H // sub), -(-W // sub)
 
 
-def split_tile_rows(npr: int, parts: int) -> List[Tuple[int, int]]:
-    """Contiguous tile-row bands balanced by tile count; empty bands dropped."""
+def split_tile_rows(npr: int, parts: int, balance_seams: bool = True) -> List[Tuple[int, int]]:
+    """Contiguous tile-row bands; empty bands dropped.  Every band but the first also recomputes
+    the tile row above its seam, so with ``balance_seams`` the bands are sized to equalise the tile rows each GPU
+    *computes* (own rows + 1 for bands 1..), not the rows it owns."""
     parts = max(1, min(parts, npr))
-    base, extra = divmod(npr, parts)
+    if not balance_seams or parts == 1:
+        base, extra = divmod(npr, parts)
+        sizes = [base + (1 if p < extra else 0) for p in range(parts)]
+    else:
+        base, extra = divmod(npr + parts - 1, parts)           # computed rows per band
+        comp = [base + (1 if p >= parts - extra else 0) for p in range(parts)]
+        sizes = [comp[0]] + [c - 1 for c in comp[1:]]
+        if min(sizes) < 1:                                     # too few rows to pay for seams: plain split
+            return split_tile_rows(npr, parts, balance_seams=False)
     out, lo = [], 0
-    for p in range(parts):
-        hi = lo + base + (1 if p < extra else 0)
-        out.append((lo, hi))
-        lo = hi
+    for n in sizes:
+        out.append((lo, lo + n))
+        lo += n
+    assert lo == npr
     return out
 
 
@@ -83,7 +93,144 @@ def band_rows_py(H: int, S: int, tile_rows: Tuple[int, int]) -> Tuple[int, int]:
     return min(H, max(0, p0 - m)), min(H, max(0, p1 - m))
 
 
-AUTO_TOLERANCE = 5e-4     # max|dp| of fp16 single-pass vs split3 on the probe tiles (4x under the 2e-3 contract)
+AUTO_TOLERANCE = 1e-3     # max|dp| budget of the chosen mode vs split3 on the probe tiles: half of the 2e-3 contract
+AUTO_PROBE_TILES = 64     # probe tiles sampled from the image being processed (corners, edges, interior)
+
+
+def _premap_apply(x: np.ndarray, premap: Optional["PreMap"]) -> np.ndarray:
+    """The float64 sample map of gather_tiles_kernel (img_as_float scale, optional rescale_intensity stretch)."""
+    x = x.astype(np.float64)
+    if premap is None:
+        return x
+    x = x * premap.in_scale
+    if premap.rescale:
+        x = np.minimum(np.maximum(x, premap.imin), premap.imax)
+        x = (x - premap.imin) / (premap.imax - premap.imin)
+        x = x * (premap.omax - premap.omin) + premap.omin
+    return x
+
+
+def probe_tile_indices(npr: int, npc: int, n: int, seed: int = 0) -> List[int]:
+    """Tile indices for calibration / parity probes: the four corner tiles, mid-edge tiles (these carry the zero
+    padding that becomes -mean/std, PartitionOfImage.py:56-63), then interior tiles on a regular grid and seeded
+    random picks.  Deterministic, no duplicates, at most n (fewer when the image has fewer tiles)."""
+    total = npr * npc
+    want = min(n, total)
+    picks: List[int] = []
+
+    def add(i: int, j: int):
+        t = min(max(i, 0), npr - 1) * npc + min(max(j, 0), npc - 1)
+        if t not in picks and len(picks) < want:
+            picks.append(t)
+
+    for i, j in ((0, 0), (0, npc - 1), (npr - 1, 0), (npr - 1, npc - 1), (0, npc // 2), (npr - 1, npc // 2),
+                 (npr // 2, 0), (npr // 2, npc - 1)):
+        add(i, j)
+    g = max(1, int(np.sqrt(max(1, (want - len(picks)) * 3 // 4))))
+    for a in range(g):
+        for b in range(g):
+            add((2 * a + 1) * npr // (2 * g), (2 * b + 1) * npc // (2 * g))
+    rng = np.random.default_rng(seed)
+    guard = 0
+    while len(picks) < want and guard < 100 * want:
+        add(int(rng.integers(npr)), int(rng.integers(npc)))
+        guard += 1
+    return picks
+
+
+def _resize_host(a: np.ndarray, out_shape: Tuple[int, int]) -> np.ndarray:
+    """skimage.transform.resize defaults on a float64 array (scipy.ndimage): only used to cut calibration tiles."""
+    from scipy import ndimage as ndi
+    fy, fx = a.shape[0] / out_shape[0], a.shape[1] / out_shape[1]
+    if fy > 1 or fx > 1:
+        a = ndi.gaussian_filter(a, (max(0.0, (fy - 1) / 2), max(0.0, (fx - 1) / 2)), mode="mirror")
+    return ndi.zoom(a, (out_shape[0] / a.shape[0], out_shape[1] / a.shape[1]), order=1, mode="mirror", grid_mode=True)
+
+
+def sample_probe_tiles(image: np.ndarray, S: int, C: int, mean: float, std: float, premap=None,
+                       n: int = AUTO_PROBE_TILES, seed: int = 0, indices: Optional[Sequence[int]] = None,
+                       infer_shape: Optional[Tuple[int, int]] = None) -> np.ndarray:
+    """Network inputs [n,S,S,C] float32 of n PI2D tiles of ``image`` ([H,W] or [C,H,W]), built on the host as
+    gather_tiles_kernel builds them on the device (PartitionOfImage.py:49-82 + UnMicst1-5.py:700): frame = premap(sample)
+    inside the image and 0 outside, (frame - mean)/std in float64, rounded to float32.  ``premap``: one PreMap or one
+    per channel.  With ``infer_shape`` the tiles are cut from the image resized to that shape (--scalingFactor); each
+    tile is resized from its own source window, which differs from the whole-image resize only by rounding and by the
+    window's mirror edge — good for calibration, not a parity reference."""
+    img = np.asarray(image)
+    planes = [img] if img.ndim == 2 else [img[c] for c in range(img.shape[0])]
+    RH, RW = planes[0].shape
+    H, W = (RH, RW) if infer_shape is None else (int(infer_shape[0]), int(infer_shape[1]))
+    scaled = (H, W) != (RH, RW)
+    m, sub, npr, npc = tile_geometry(H, W, S)
+    idx = list(indices) if indices is not None else probe_tile_indices(npr, npc, n, seed)
+    out = np.empty((len(idx), S, S, C), dtype=np.float32)
+    for k, t in enumerate(idx):
+        ti, tj = divmod(int(t), npc)
+        r0, c0 = ti * sub - m, tj * sub - m                       # image coordinates of the tile's first pixel
+        ra, rb, ca, cb = max(r0, 0), min(r0 + S, H), max(c0, 0), min(c0 + S, W)
+        for c in range(C):
+            frame = np.zeros((S, S), dtype=np.float64)
+            if rb > ra and cb > ca:
+                src = planes[0 if len(planes) == 1 else c]
+                pm = premap[c] if isinstance(premap, (list, tuple)) else premap
+                if not scaled:
+                    frame[ra - r0:rb - r0, ca - c0:cb - c0] = _premap_apply(src[ra:rb, ca:cb], pm)
+                else:
+                    # source window of the tile (+ a margin for the interpolation taps), resized with the global zoom
+                    zy, zx = RH / H, RW / W
+                    pad = 8
+                    sa, sb = max(0, int(ra * zy) - pad), min(RH, int(np.ceil(rb * zy)) + pad)
+                    ta, tb = max(0, int(ca * zx) - pad), min(RW, int(np.ceil(cb * zx)) + pad)
+                    oa, ob = int(round(sa / zy)), int(round(sb / zy))
+                    pa, pb = int(round(ta / zx)), int(round(tb / zx))
+                    win = src[sa:sb, ta:tb].astype(np.float64) * (pm.in_scale if pm is not None else 1.0)
+                    up = _resize_host(win, (max(ob - oa, 1), max(pb - pa, 1)))
+                    sub_img = up[np.clip(np.arange(ra, rb) - oa, 0, up.shape[0] - 1)][:, np.clip(np.arange(ca, cb) - pa, 0, up.shape[1] - 1)]
+                    if pm is not None and pm.rescale:
+                        sub_img = np.minimum(np.maximum(sub_img, pm.imin), pm.imax)
+                        sub_img = (sub_img - pm.imin) / (pm.imax - pm.imin) * (pm.omax - pm.omin) + pm.omin
+                    frame[ra - r0:rb - r0, ca - c0:cb - c0] = sub_img
+            out[k, :, :, c] = ((frame - mean) / std).astype(np.float32)
+    return out
+
+
+def tensor_ops(model: Model) -> List[Tuple[int, str]]:
+    """(op index, name) of every op the tensor path runs in the split plan: the candidates of UMX_PREC_MIXED."""
+    out = []
+    for line in describe_plan(model, "split3"):
+        f = line.split()
+        if len(f) > 3 and f[1] == "conv" and f[3] == "tensor":
+            out.append((int(f[0]), f[2]))
+    return out
+
+
+def choose_single_mask(errs: Dict[int, float], costs: Dict[int, float], budget: float, exclude: Sequence[int] = ()) -> int:
+    """Error-budgeted layer selection: the subset of ops to run with one MMA per product that saves the most time
+    while the predicted max|dp| — the per-layer contributions added in quadrature (rounding errors of different layers
+    are independent) — stays inside ``budget``.  Exact over all subsets up to 20 candidates, ratio-greedy beyond."""
+    ops = [i for i in errs if i not in exclude and costs.get(i, 0.0) > 0.0]
+    if not ops:
+        return 0
+    b2 = budget * budget
+    if len(ops) <= 20:
+        best_mask, best_gain = 0, 0.0
+        e2 = [errs[i] ** 2 for i in ops]
+        cs = [costs[i] for i in ops]
+        for sub in range(1, 1 << len(ops)):
+            e, g = 0.0, 0.0
+            for k in range(len(ops)):
+                if sub >> k & 1:
+                    e += e2[k]
+                    g += cs[k]
+            if e <= b2 and g > best_gain:
+                best_gain, best_mask = g, sub
+        return sum(1 << ops[k] for k in range(len(ops)) if best_mask >> k & 1)
+    mask, e = 0, 0.0
+    for i in sorted(ops, key=lambda i: errs[i] ** 2 / costs[i]):
+        if e + errs[i] ** 2 <= b2:
+            e += errs[i] ** 2
+            mask |= 1 << i
+    return mask
 
 
 def mask_to_reserved(mask: int) -> Tuple[int, int]:
@@ -126,58 +273,95 @@ def describe_plan(model: Model, precision: str = "default", single_mask: int = 0
     return buf.value.decode().splitlines()
 
 
+def calibrate(model: Model, device: int = 0, probe_tiles: Optional[np.ndarray] = None, budget: float = AUTO_TOLERANCE,
+              verbose: bool = False) -> Tuple[str, int, Dict]:
+    """Pick the cheapest arithmetic that keeps max|dp| vs the hi/lo split within ``budget`` on ``probe_tiles``
+    (tiles of the image about to be processed: sample_probe_tiles).  Returns (precision, single_mask, report).
+
+    1. all-single within budget -> 'single'.
+    2. otherwise measure, once per tensor-path layer, the max|dp| that running only this layer with one MMA per product
+       causes (its error contribution) and the time it saves (profiled single vs split pass), choose the subset with
+       the largest saving whose contributions, added in quadrature, fit 80 % of the budget (choose_single_mask), then
+       verify the chosen mask as a whole and drop the least profitable layers until the measured error fits.
+    """
+    S, C = int(model.hp["imSize"]), int(model.hp["nChannels"])
+    if probe_tiles is None:
+        rng = np.random.default_rng(2024)
+        probe_tiles = rng.normal(size=(16, S, S, C)).astype(np.float32)
+    probe_tiles = np.ascontiguousarray(probe_tiles, dtype=np.float32)
+    n_time = max(len(probe_tiles), min(1024, (1 << 22) // (S * S)))        # enough tiles for meaningful kernel times
+    reps = -(-n_time // len(probe_tiles))
+    timing_tiles = np.concatenate([probe_tiles] * reps)[:n_time] if reps > 1 else probe_tiles
+    batch = max(64, n_time)
+
+    def profile_of(e: "Engine") -> List[Dict]:
+        e.forward_tiles(timing_tiles)                 # warm-up
+        e.profile_enable(True)
+        e.forward_tiles(timing_tiles)
+        prof = e.profile_read()
+        e.profile_enable(False)
+        return prof
+
+    with Engine(model, device, "split3", batch) as ref:
+        want = ref.forward_tiles(probe_tiles)
+        prof_split = profile_of(ref)
+
+    def err_of(prec: str, mask: int = 0) -> float:
+        with Engine(model, device, prec, batch, single_mask=mask) as e:
+            return float(np.abs(e.forward_tiles(probe_tiles) - want).max())
+
+    with Engine(model, device, "single", batch) as es:
+        d_single = float(np.abs(es.forward_tiles(probe_tiles) - want).max())
+        prof_single = profile_of(es)
+    report: Dict = {"probe_tiles": int(len(probe_tiles)), "budget": budget, "single_vs_split3_max_abs_dp": d_single,
+                    "tolerance": budget}
+    if d_single <= budget:
+        report["chosen"] = "single"
+        return "single", 0, report
+    cands = [(i, n) for i, n in tensor_ops(model) if i < 64]
+    errs: Dict[int, float] = {}
+    costs: Dict[int, float] = {}
+    layers = []
+    for i, name in cands:
+        errs[i] = err_of("mixed", 1 << i)
+        costs[i] = max(0.0, prof_split[i]["ms"] - prof_single[i]["ms"])
+        layers.append({"op": i, "name": name, "dp_alone": errs[i], "split_ms": round(prof_split[i]["ms"], 4),
+                       "single_ms": round(prof_single[i]["ms"], 4)})
+        if verbose:
+            print(f"[calibrate] {name:14s} dp_alone {errs[i]:.2e}  split {prof_split[i]['ms']:.3f} ms  single {prof_single[i]['ms']:.3f} ms", flush=True)
+    mask = choose_single_mask(errs, costs, 0.8 * budget)
+    d_mixed = err_of("mixed", mask) if mask else 0.0
+    dropped = []
+    while mask and d_mixed > budget:
+        worst = max((i for i in errs if mask >> i & 1), key=lambda i: errs[i] ** 2 / max(costs[i], 1e-9))
+        mask &= ~(1 << worst)
+        dropped.append(worst)
+        d_mixed = err_of("mixed", mask) if mask else 0.0
+    names = dict(cands)
+    report.update({"layers": layers, "single_layers": [names[i] for i in names if mask >> i & 1],
+                   "dropped_after_verify": [names[i] for i in dropped], "mixed_vs_split3_max_abs_dp": d_mixed,
+                   "predicted_quadrature_dp": float(np.sqrt(sum(errs[i] ** 2 for i in errs if mask >> i & 1))),
+                   "single_mask": mask, "chosen": "mixed" if mask else "split3"})
+    return ("mixed" if mask else "split3"), mask, report
+
+
 class Engine:
     """precision: 'default'/'split3' (fp16 hi/lo split, ~fp32 accurate, always within the 2e-3 contract),
     'single' (one fp16 MMA per product: ~3x less tensor work, accuracy depends on how steep the
     model's softmax is), 'mixed' (per layer: ``single_mask`` bit i = op i of ``profile_read`` runs single),
-    'fp32' (CUDA cores only), or 'auto': calibrate on probe tiles against 'split3' — keep 'single' if it
-    stays within AUTO_TOLERANCE, otherwise switch layers to single greedily (most expensive first) for as
-    long as the probe stays within the tolerance ('mixed'), which may end at plain 'split3'."""
+    'fp32' (CUDA cores only), or 'auto': ``calibrate`` on ``probe_tiles`` (tiles of the image to be processed, see
+    ``sample_probe_tiles``; seeded noise tiles when none are given) against 'split3' with the AUTO_TOLERANCE budget —
+    all-'single' if that fits, otherwise the error-budgeted per-layer 'mixed' selection, which may end at 'split3'."""
 
     def __init__(self, model: Model, device: int = 0, precision: str = "default", max_batch_tiles: int = 0,
                  probe_tiles: Optional[np.ndarray] = None, single_mask: int = 0):
         self.auto_report = None
         self.single_mask = 0
         if precision == "auto":
-            probe_batch = 64
-            ref = Engine(model, device, "split3", probe_batch)
-            if probe_tiles is None:
-                rng = np.random.default_rng(2024)
-                probe_tiles = rng.normal(size=(16, ref.S, ref.S, ref.C)).astype(np.float32)
-            want = ref.forward_tiles(probe_tiles)
-
-            def err_of(prec: str, mask: int = 0) -> float:
-                with Engine(model, device, prec, probe_batch, single_mask=mask) as e:
-                    return float(np.abs(e.forward_tiles(probe_tiles) - want).max())
-
-            d_single = err_of("single")
-            report = {"single_vs_split3_max_abs_dp": d_single, "tolerance": AUTO_TOLERANCE}
-            if d_single <= AUTO_TOLERANCE:
-                chosen, mask = "single", 0
-            else:
-                # cost per op from one profiled pass of the split engine; candidates = tensor-path layers
-                ref.profile_enable(True)
-                ref.forward_tiles(probe_tiles)
-                prof = ref.profile_read()
-                ref.profile_enable(False)
-                order = sorted((i for i, p in enumerate(prof) if p["flops"] > 0 and p["launches"] > 0 and i < 64),
-                               key=lambda i: -prof[i]["ms"])
-                mask, kept, d_mixed = 0, [], 0.0
-                for i in order:
-                    d = err_of("mixed", mask | (1 << i))
-                    if d == d_mixed:
-                        continue                              # the bit changes nothing: not a tensor-path layer
-                    if d <= AUTO_TOLERANCE:
-                        mask |= 1 << i
-                        kept.append(prof[i]["name"])
-                        d_mixed = d
-                chosen = "mixed" if mask else "split3"
-                report.update({"single_layers": kept, "mixed_vs_split3_max_abs_dp": d_mixed})
-            ref.close()
+            chosen, mask, report = calibrate(model, device, probe_tiles)
             final = Engine(model, device, chosen, max_batch_tiles, single_mask=mask)
             self.__dict__.update(final.__dict__)
             final._h = None
-            report["chosen"] = chosen
             self.auto_report = report
             return
         L = lib()
@@ -249,19 +433,52 @@ class Engine:
         check(lib().umx_band_rows(self._h, H, tr0, tr1, C.byref(r0), C.byref(r1)))
         return r0.value, r1.value
 
+    def band_out_rows(self, infer_h: int, raw_h: int, tile_rows: Optional[Tuple[int, int]] = None) -> Tuple[int, int]:
+        """Raw-grid rows a tile-row band writes with ``cli_quant`` when the network runs at ``infer_h`` rows."""
+        r0, r1 = C.c_int32(0), C.c_int32(0)
+        tr0, tr1 = tile_rows if tile_rows else (0, 0)
+        check(lib().umx_band_out_rows(self._h, infer_h, tr0, tr1, raw_h, C.byref(r0), C.byref(r1)))
+        return r0.value, r1.value
+
+    def resample_minmax(self, plane: np.ndarray, out_shape: Tuple[int, int], in_scale: float = 1.0) -> Tuple[float, float]:
+        """(min, max) of skimage.transform.resize(img_as_float(plane), out_shape), computed on the GPU."""
+        a = np.ascontiguousarray(plane)
+        if a.ndim != 2 or a.dtype not in _NP2UMX:
+            raise TypeError("plane must be a 2-D uint8/uint16/float32/float64 array")
+        lo, hi = C.c_double(0), C.c_double(0)
+        with self._lock:
+            check(lib().umx_resample_minmax(self._h, a.ctypes.data, _NP2UMX[a.dtype], a.shape[0], a.shape[1],
+                                            int(out_shape[0]), int(out_shape[1]), float(in_scale), C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
     def infer_ptr(self, img_ptr: int, dtype: int, n_planes: int, H: int, W: int, plane_stride: int,
                   mean: float, std: float, out_u8_ptr: int = 0, out_f32_ptr: int = 0,
                   tile_rows: Optional[Tuple[int, int]] = None, premap: Optional[PreMap] = None,
                   out_plane_stride: int = 0, out_row_base: int = 0, precision: str = "default",
-                  no_sync: bool = False) -> None:
-        """Raw-pointer form (host pageable / pinned or device memory — the library detects which)."""
+                  no_sync: bool = False, infer_shape: Optional[Tuple[int, int]] = None, cli_quant: bool = False,
+                  continue_prev: bool = False, stitch_mode: str = "accumulate") -> None:
+        """Raw-pointer form (host pageable / pinned or device memory — the library detects which).
+        ``infer_shape``: run the network on the image resized to this (rows, cols) (--scalingFactor);
+        ``cli_quant``: out_u8 = the page the reference CLI writes ([K,H,W] of the raw grid, quantised twice)."""
         o = _lib.umx_opts()
         if tile_rows:
             o.tile_row0, o.tile_row1 = int(tile_rows[0]), int(tile_rows[1])
         o.precision = _lib.PRECISIONS[precision]
-        o.flags = _lib.UMX_F_NO_SYNC if no_sync else 0
-        pm = premap.to_c() if premap else None
-        o.premap = C.pointer(pm) if pm is not None else None
+        o.flags = ((_lib.UMX_F_NO_SYNC if no_sync else 0) | (_lib.UMX_F_CLI_QUANT if cli_quant else 0) |
+                   (_lib.UMX_F_CONTINUE if continue_prev else 0) | (_lib.UMX_F_STITCH_REPLACE if stitch_mode == "replace" else 0))
+        if stitch_mode not in ("accumulate", "replace"):
+            raise ValueError("stitch_mode must be 'accumulate' or 'replace' (PartitionOfImage.py:92-100)")
+        if infer_shape is not None:
+            o.infer_h, o.infer_w = int(infer_shape[0]), int(infer_shape[1])
+        if isinstance(premap, (list, tuple)):                 # one map per image plane (unmicst-duo)
+            if len(premap) != self.C:
+                raise ValueError(f"{len(premap)} premaps for a network with {self.C} input channels")
+            pm = (_lib.umx_premap * len(premap))(*[q.to_c() for q in premap])
+            o.premap = C.cast(pm, C.POINTER(_lib.umx_premap))
+            o.flags |= _lib.UMX_F_PREMAP_PER_PLANE
+        else:
+            pm = premap.to_c() if premap else None
+            o.premap = C.pointer(pm) if pm is not None else None
         o.out_plane_stride = int(out_plane_stride)
         o.out_row_base = int(out_row_base)
         with self._lock:
@@ -271,10 +488,14 @@ class Engine:
     def infer_image(self, image: np.ndarray, mean: Optional[float] = None, std: Optional[float] = None,
                     premap: Optional[PreMap] = None, want_u8: bool = True, want_f32: bool = False,
                     tile_rows: Optional[Tuple[int, int]] = None, out_u8: Optional[np.ndarray] = None,
-                    out_f32: Optional[np.ndarray] = None, precision: str = "default"):
-        """image [H,W] or [C,H,W] (uint8/uint16/float32/float64) -> (u8 [K,H,W] | None, f32 [K,H,W] | None).
+                    out_f32: Optional[np.ndarray] = None, precision: str = "default",
+                    infer_shape: Optional[Tuple[int, int]] = None, cli_quant: bool = False, stitch_mode: str = "accumulate"):
+        """image [H,W] or [C,H,W] (uint8/uint16/float32/float64) -> (u8 [K,h,w] | None, f32 [K,h,w] | None).
 
-        With ``tile_rows`` only the image rows of that band are written (into full-size outputs)."""
+        With ``tile_rows`` only the image rows of that band are written (into full-size outputs).
+        ``infer_shape`` = (rows, cols) the network runs at (the image is resized on the GPU with
+        skimage.transform.resize semantics, UnMicst1-5.py:813-815); outputs then have that shape, unless
+        ``cli_quant`` asks for the reference CLI's page: resized back to [K,H,W] and quantised twice (:848-853)."""
         img = np.ascontiguousarray(image)
         if img.dtype not in _NP2UMX:
             raise TypeError(f"unsupported image dtype {img.dtype}")
@@ -286,15 +507,79 @@ class Engine:
             raise ValueError("image must be [H,W] or [C,H,W]")
         mean = self.model.mean if mean is None else mean
         std = self.model.std if std is None else std
+        oh, ow = (H, W) if (cli_quant or infer_shape is None) else (int(infer_shape[0]), int(infer_shape[1]))
+        if cli_quant:
+            want_u8, want_f32 = True, False
         if want_u8 and out_u8 is None:
-            out_u8 = np.zeros((self.K, H, W), dtype=np.uint8)
+            out_u8 = np.zeros((self.K, oh, ow), dtype=np.uint8)
         if want_f32 and out_f32 is None:
-            out_f32 = np.zeros((self.K, H, W), dtype=np.float32)
+            out_f32 = np.zeros((self.K, oh, ow), dtype=np.float32)
         self.infer_ptr(img.ctypes.data, _NP2UMX[img.dtype], planes, H, W, H * W, mean, std,
                        out_u8.ctypes.data if out_u8 is not None else 0,
                        out_f32.ctypes.data if out_f32 is not None else 0,
-                       tile_rows=tile_rows, premap=premap, precision=precision)
+                       tile_rows=tile_rows, premap=premap, precision=precision, infer_shape=infer_shape, cli_quant=cli_quant,
+                       stitch_mode=stitch_mode)
         return out_u8, out_f32
+
+    def stream_image(self, image: np.ndarray, mean: Optional[float] = None, std: Optional[float] = None,
+                     premap=None, chunk_tile_rows: int = 0, infer_shape: Optional[Tuple[int, int]] = None,
+                     cli_quant: bool = False):
+        """Generator over row bands of the uint8 maps: yields (row0, row1, u8 [K, row1-row0, w]) as each band of
+        ``chunk_tile_rows`` tile rows leaves the GPU, so a consumer (the BigTIFF writer, UnMicst1-5.py:852-862) works on
+        band i while band i+1 is computed.  Bands continue each other on the device (UMX_F_CONTINUE): nothing is
+        recomputed and the bytes equal one whole-image call."""
+        img = np.ascontiguousarray(image)
+        if img.dtype not in _NP2UMX:
+            raise TypeError(f"unsupported image dtype {img.dtype}")
+        planes, (H, W) = (1, img.shape) if img.ndim == 2 else (img.shape[0], img.shape[1:])
+        mean = self.model.mean if mean is None else mean
+        std = self.model.std if std is None else std
+        ih, iw = (H, W) if infer_shape is None else (int(infer_shape[0]), int(infer_shape[1]))
+        _, _, npr, npc = tile_geometry(ih, iw, self.S)
+        if chunk_tile_rows <= 0:
+            chunk_tile_rows = max(1, min(npr, -(-8192 // npc)))           # ~8k tiles per band
+        ow = W if cli_quant else iw
+        for a in range(0, npr, chunk_tile_rows):
+            b = min(npr, a + chunk_tile_rows)
+            r0, r1 = self.band_out_rows(ih, H, (a, b)) if cli_quant else self.band_rows(ih, (a, b))
+            buf = np.empty((self.K, max(r1 - r0, 0), ow), dtype=np.uint8)
+            self.infer_ptr(img.ctypes.data, _NP2UMX[img.dtype], planes, H, W, H * W, mean, std, out_u8_ptr=buf.ctypes.data,
+                           tile_rows=(a, b), premap=premap, out_plane_stride=buf.shape[1] * ow, out_row_base=r0,
+                           infer_shape=infer_shape, cli_quant=cli_quant, continue_prev=a > 0)
+            if r1 > r0:
+                yield r0, r1, buf
+
+    # -- many small images per launch (TMA cores) ---------------------------------------------------------
+    def infer_images(self, images: Sequence[np.ndarray], premaps: Optional[Sequence[Optional[PreMap]]] = None,
+                     mean: Optional[float] = None, std: Optional[float] = None, want_f32: bool = False,
+                     cli_quant: bool = False) -> List[np.ndarray]:
+        """``umx_infer_images``: every image ([H,W] or [C,H,W]) through the resident model, tiles of several images
+        sharing each network launch (the dearray loop of batchUNet2DTMACycif.py:539-569).  Returns one uint8 [K,H,W]
+        (or float32 with ``want_f32``) per image, equal to ``infer_image`` on each."""
+        n = len(images)
+        arr = (_lib.umx_image * n)()
+        keep, outs = [], []
+        for i, im in enumerate(images):
+            a = np.ascontiguousarray(im)
+            if a.dtype not in _NP2UMX:
+                raise TypeError(f"unsupported image dtype {a.dtype}")
+            planes, (H, W) = (1, a.shape) if a.ndim == 2 else (a.shape[0], a.shape[1:])
+            out = np.zeros((self.K, H, W), dtype=np.float32 if want_f32 else np.uint8)
+            pm = premaps[i].to_c() if premaps is not None and premaps[i] is not None else None
+            keep.append((a, pm))
+            outs.append(out)
+            arr[i].img, arr[i].dtype, arr[i].n_planes, arr[i].H, arr[i].W = a.ctypes.data, _NP2UMX[a.dtype], planes, H, W
+            arr[i].plane_stride = H * W
+            arr[i].premap = C.pointer(pm) if pm is not None else None
+            if want_f32:
+                arr[i].out_f32 = out.ctypes.data
+            else:
+                arr[i].out_u8 = out.ctypes.data
+        mean = self.model.mean if mean is None else mean
+        std = self.model.std if std is None else std
+        with self._lock:
+            check(lib().umx_infer_images(self._h, arr, n, float(mean), float(std), _lib.UMX_F_CLI_QUANT if cli_quant else 0))
+        return outs
 
     # -- instrumentation -----------------------------------------------------------------------
     def set_stream(self, cuda_stream: int) -> None:
@@ -332,33 +617,59 @@ class MultiEngine:
     """The same model on several GPUs of one box; an image is cut into contiguous tile-row
     bands, one per GPU, each driven by its own host thread (ctypes releases the GIL).
     Every band recomputes the single tile row above its seam, so band outputs are
-    bit-identical to the 1-GPU result and no device-to-device exchange exists."""
+    bit-identical to the 1-GPU result and no device-to-device exchange exists.
+    precision 'auto' calibrates once (on the first device) and builds every engine with that result, so all bands
+    run the same arithmetic."""
 
-    def __init__(self, model: Model, devices: Sequence[int], precision: str = "default", max_batch_tiles: int = 0):
+    def __init__(self, model: Model, devices: Sequence[int], precision: str = "default", max_batch_tiles: int = 0,
+                 probe_tiles: Optional[np.ndarray] = None, single_mask: int = 0):
         if not devices:
             raise ValueError("MultiEngine needs at least one device")
-        self.engines = [Engine(model, d, precision, max_batch_tiles) for d in devices]
+        self.auto_report = None
+        if precision == "auto":
+            precision, single_mask, self.auto_report = calibrate(model, devices[0], probe_tiles)
+        self.engines = [Engine(model, d, precision, max_batch_tiles, single_mask=single_mask) for d in devices]
         self.model = model
+        self.precision, self.single_mask = self.engines[0].precision, self.engines[0].single_mask
         self.S, self.C, self.K = self.engines[0].S, self.engines[0].C, self.engines[0].K
 
     def close(self) -> None:
         for e in self.engines:
             e.close()
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def launch_count(self) -> int:
+        return sum(e.launch_count for e in self.engines)
+
+    def resample_minmax(self, plane, out_shape, in_scale: float = 1.0):
+        return self.engines[0].resample_minmax(plane, out_shape, in_scale)
+
     def infer_image(self, image: np.ndarray, mean=None, std=None, premap=None, want_u8=True, want_f32=False,
-                    precision: str = "default"):
+                    precision: str = "default", infer_shape: Optional[Tuple[int, int]] = None, cli_quant: bool = False,
+                    stitch_mode: str = "accumulate"):
         img = np.ascontiguousarray(image)
         H, W = img.shape[-2:]
-        _, _, npr, _ = tile_geometry(H, W, self.S)
+        ih, iw = (H, W) if infer_shape is None else (int(infer_shape[0]), int(infer_shape[1]))
+        _, _, npr, _ = tile_geometry(ih, iw, self.S)
         bands = split_tile_rows(npr, len(self.engines))
-        out_u8 = np.zeros((self.K, H, W), dtype=np.uint8) if want_u8 else None
-        out_f32 = np.zeros((self.K, H, W), dtype=np.float32) if want_f32 else None
+        oh, ow = (H, W) if cli_quant else (ih, iw)
+        if cli_quant:
+            want_u8, want_f32 = True, False
+        out_u8 = np.zeros((self.K, oh, ow), dtype=np.uint8) if want_u8 else None
+        out_f32 = np.zeros((self.K, oh, ow), dtype=np.float32) if want_f32 else None
         errs: List[BaseException] = []
 
         def work(eng: Engine, band):
             try:
                 eng.infer_image(img, mean, std, premap, want_u8, want_f32, tile_rows=band, out_u8=out_u8,
-                                out_f32=out_f32, precision=precision)
+                                out_f32=out_f32, precision=precision, infer_shape=infer_shape, cli_quant=cli_quant,
+                                stitch_mode=stitch_mode)
             except BaseException as ex:  # re-raised on the caller's thread
                 errs.append(ex)
 

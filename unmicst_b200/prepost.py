@@ -1,10 +1,11 @@
 """Host-side pre/post-processing of the CLI scripts (everything around the GPU hot path).
 
-Mirrors UnMicst1-5.py:807-825,848-862 / UnMicst.py:621-660.  At scalingFactor 1 nothing is
-resampled on the host: the raw integer samples go to the GPU together with a PreMap
-(img_as_float scale + optional rescale_intensity stretch, evaluated in float64 in-kernel).
-For other factors the resampling follows scikit-image's ``resize`` defaults, restated on
-scipy.ndimage (bilinear, half-pixel grid, mirror boundary, Gaussian anti-aliasing on shrink).
+Mirrors UnMicst1-5.py:807-825,848-862 / UnMicst.py:621-660.  Nothing is resampled on the host: the raw
+integer samples go to the GPU together with a PreMap (img_as_float scale + optional rescale_intensity
+stretch, evaluated in float64 in-kernel) and, for --scalingFactor != 1, the size to resize them to; the
+library applies scikit-image's ``resize`` defaults (bilinear, half-pixel grid, mirror boundary, Gaussian
+anti-aliasing on shrink) on the fly and resizes the uint8 pages back.  ``resample`` below restates the same
+on scipy.ndimage for the one case that needs the whole resized image on the host (--outlier percentiles).
 """
 from __future__ import annotations
 
@@ -47,27 +48,33 @@ def resample(img: np.ndarray, out_shape: Tuple[int, int]) -> np.ndarray:
     return np.clip(out, lo, hi)
 
 
-def network_input(raw: np.ndarray, factor: float, stretch: bool, outlier: float = -1):
-    """What `singleImageInference` is fed, as (array, PreMap).
+def network_input(raw: np.ndarray, factor: float, stretch: bool, outlier: float = -1, engine=None):
+    """What `singleImageInference` is fed, as (samples, PreMap, infer_shape).
 
-    stretch=False: solo (`cells = I`, UnMicst1-5.py:816); stretch=True: legacy / duo / Cyto2
-    (rescale_intensity to (0, 0.983) with max or the --outlier percentile, :817-821)."""
+    The raw integer samples always go to the GPU as they are; ``infer_shape`` (None at scalingFactor 1) is the size the
+    library resizes them to on the fly (UnMicst1-5.py:813-815), the PreMap carries img_as_float and, with
+    ``stretch`` (legacy / duo / Cyto2: rescale_intensity of the RESIZED image to (0, 0.983) with its max or the
+    --outlier percentile, :817-821), the in_range.  solo feeds the un-stretched image (`cells = I`, :816).
+    With an ``engine`` the min/max of the resized image come from the GPU (umx_resample_minmax); percentiles and
+    engine-less calls resample on the host."""
     raw = coerce_raw(raw)
     scale = as_float_scale(raw.dtype)
     shape = scaled_shape(raw.shape, factor)
-    if shape == raw.shape:
-        arr, in_scale = raw, scale                       # resize is the identity: keep the integers
-        if stretch:
-            lo = float(raw.min()) * scale
-            top = float(raw.max()) * scale if outlier == -1 else float(np.percentile(raw.astype(np.float64) * scale, outlier))
+    infer_shape = None if shape == raw.shape else shape
+    if not stretch:
+        return raw, PreMap(in_scale=scale, rescale=False), infer_shape
+    if infer_shape is None:
+        lo = float(raw.min()) * scale
+        top = float(raw.max()) * scale if outlier == -1 else float(np.percentile(raw.astype(np.float64) * scale, outlier))
+    elif outlier == -1 and engine is not None and raw.dtype in (np.uint8, np.uint16, np.float32, np.float64):
+        lo, top = engine.resample_minmax(raw, shape, scale)
     else:
-        arr, in_scale = resample(raw.astype(np.float64) * scale, shape), 1.0
-        if stretch:
-            lo = float(arr.min())
-            top = float(arr.max()) if outlier == -1 else float(np.percentile(arr, outlier))
-    if stretch and top > lo:
-        return arr, PreMap(in_scale=in_scale, rescale=True, imin=lo, imax=top, omin=0.0, omax=0.983)
-    return arr, PreMap(in_scale=in_scale, rescale=False)
+        arr = resample(raw.astype(np.float64) * scale, shape)
+        lo = float(arr.min())
+        top = float(arr.max()) if outlier == -1 else float(np.percentile(arr, outlier))
+    if top > lo:
+        return raw, PreMap(in_scale=scale, rescale=True, imin=lo, imax=top, omin=0.0, omax=0.983), infer_shape
+    return raw, PreMap(in_scale=scale, rescale=False), infer_shape
 
 
 # uint8 -> resize (img_as_float: v * (1/255)) -> uint8(255 * x): the reference quantises twice

@@ -256,6 +256,10 @@ class BigTiffWriter:
         p = self._page
         if p["rows"] != p["h"]:
             raise TiffError(f"page has {p['rows']} of {p['h']} rows")
+        self._write_ifd(p)
+        self._page = None
+
+    def _write_ifd(self, p: Dict) -> None:
         nbytes = p["h"] * p["w"] * p["dt"].itemsize
         fmt = {"u": 1, "i": 2, "f": 3}[p["dt"].kind]
         tags: List[Tuple[int, int, int, object]] = [
@@ -267,6 +271,7 @@ class BigTiffWriter:
         if not self.big and (p["data_off"] + nbytes) >= 2 ** 32:
             raise TiffError("classic TIFF cannot exceed 4 GiB; use bigtiff")
         extra = b""
+        self.f.seek(0, os.SEEK_END)
         pos = self.f.tell()
         if pos % 16:
             self.f.write(b"\0" * (16 - pos % 16))
@@ -297,7 +302,40 @@ class BigTiffWriter:
         self.f.write(struct.pack("<Q" if self.big else "<I", ifd_off))
         self.f.seek(end)
         self._link_pos = ifd_off + hdr + n * esz
-        self._page = None
+
+    # -- several pages streamed side by side: the K class maps of one image arrive band by band (rows r0..r1 of every
+    # page at once), so the data areas of all pages are reserved first and rows are written in place as they come
+    def begin_pages(self, n_pages: int, height: int, width: int, dtype=np.uint8) -> None:
+        if self._page is not None or getattr(self, "_pages", None):
+            raise TiffError("previous page not finished")
+        self.f.seek(0, os.SEEK_END)
+        pos = self.f.tell()
+        if pos % 16:
+            self.f.write(b"\0" * (16 - pos % 16))
+        dt = np.dtype(dtype)
+        nbytes = height * width * dt.itemsize
+        stride = (nbytes + 15) & ~15
+        base = self.f.tell()
+        self._pages = [dict(h=height, w=width, dt=dt, data_off=base + i * stride, rows=0, desc=None, seen=np.zeros(height, bool))
+                       for i in range(n_pages)]
+        self.f.truncate(base + n_pages * stride)          # reserves (sparse) space; rows land by seek + write
+
+    def write_page_rows(self, page: int, row0: int, rows: np.ndarray) -> None:
+        p = self._pages[page]
+        a = np.ascontiguousarray(rows, dtype=p["dt"])
+        if a.ndim != 2 or a.shape[1] != p["w"] or row0 < 0 or row0 + a.shape[0] > p["h"]:
+            raise TiffError("rows do not fit the page")
+        self.f.seek(p["data_off"] + row0 * p["w"] * p["dt"].itemsize)
+        self.f.write(a.tobytes())
+        p["seen"][row0:row0 + a.shape[0]] = True
+
+    def end_pages(self) -> None:
+        for p in self._pages:
+            if not p["seen"].all():
+                raise TiffError(f"page is missing {int((~p['seen']).sum())} of {p['h']} rows")
+        for p in self._pages:
+            self._write_ifd(p)
+        self._pages = None
 
     def write_page(self, array: np.ndarray, description: Optional[str] = None) -> None:
         a = np.asarray(array)
@@ -308,7 +346,7 @@ class BigTiffWriter:
         self.end_page()
 
     def close(self) -> None:
-        if self._page is not None:
+        if self._page is not None or getattr(self, "_pages", None):
             raise TiffError("page not finished")
         self.f.close()
 
