@@ -238,7 +238,7 @@ def choose_model(name: str, probe_of):
         return modelzoo.load_model(d), None
     base = modelzoo.synthetic_model(name, seed=0, logit_gain=1.0)
     taps = {}
-    oracle_forward(base, taps)(probe_of(base)[:16])
+    oracle_forward(base, taps)(probe_of(base))             # all probe tiles: the steepness is that of the hardest one
     gain = float(TARGET_MAX_LOGIT / max(1e-6, np.abs(taps["logits"]).max()))
     return modelzoo.synthetic_model(name, seed=0, logit_gain=gain), gain
 
@@ -332,24 +332,24 @@ def run_workload(name: str, args, steps: int, warmup: int, main: bool, reuse=Non
     if rank == 0:
         host_threads(world)
         if reuse and reuse.get("model_name") == model_name:
-            model, gain, prec, mask, auto = reuse["model"], reuse["gain"], reuse["prec"], reuse["mask"], reuse["auto"]
+            model, gain, prec, terms, auto = reuse["model"], reuse["gain"], reuse["prec"], reuse["terms"], reuse["auto"]
             probe_of(model)
         else:
             model, gain = choose_model(model_name, probe_of)
-            prec, mask, auto = args.precision, 0, None
+            prec, terms, auto = args.precision, {}, None
             if prec == "auto":
-                prec, mask, auto = calibrate(model, local, probe_of(model))
+                prec, terms, auto = calibrate(model, local, probe_of(model))
             elif prec == "default":
                 prec = "split3"
-        plan = dict(gain=gain, prec=prec, mask=mask)
+        plan = dict(gain=gain, prec=prec, terms=terms)
     plan = bcast(plan, world)
     if rank != 0:
         from unmicst_b200 import modelzoo
         d = os.path.join(ROOT, "tests", "golden", "models", model_name)
         model = modelzoo.load_model(d) if plan["gain"] is None else modelzoo.synthetic_model(model_name, seed=0, logit_gain=plan["gain"])
         auto = None
-    gain, prec, mask = plan["gain"], plan["prec"], plan["mask"]
-    eng = Engine(model, device=local, precision=prec, max_batch_tiles=args.max_batch, single_mask=mask)
+    gain, prec, terms = plan["gain"], plan["prec"], plan["terms"]
+    eng = Engine(model, device=local, precision=prec, max_batch_tiles=args.max_batch, op_terms=terms)
     K = eng.K
 
     # ---- parity of the timed engine against the oracle on tiles of this image
@@ -518,7 +518,7 @@ def run_workload(name: str, args, steps: int, warmup: int, main: bool, reuse=Non
     out = None
     if rank == 0:
         dtype = {"fp32": "f32", "split3": "f16 hi/lo split x3 MMA, f32 accumulate", "single": "f16, f32 accumulate",
-                 "mixed": "f16 (per layer: 1 MMA or hi/lo split x3), f32 accumulate"}[prec]
+                 "mixed": "f16 (per layer and concat source: 1 MMA, or hi/lo split with 1-2 correction MMAs), f32 accumulate"}[prec]
         out = {
             "metric": "megapixels/sec of K-class probability map", "value": value, "unit": "MP/s",
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
@@ -529,6 +529,7 @@ def run_workload(name: str, args, steps: int, warmup: int, main: bool, reuse=Non
                        "H": IH, "W": IW, "raw_H": H, "raw_W": W, "scaling_factor": scale, "tiles": npr * npc, "tile": S,
                        "precision": prec, "precision_requested": args.precision,
                        "single_mma_layers": (auto or {}).get("single_layers") if prec == "mixed" else None,
+                       "partial_split_layers": {k: v for k, v in (auto or {}).get("op_terms", {}).items() if v not in ([0, 0], [3, 3])} if prec == "mixed" else None,
                        "l2": "inputs + activations per step >> 126 MB L2, no explicit flush",
                        "parallelism": f"tile-row bands x{world} balanced by computed rows (own + seam), no collective"},
             "clocks": clk.summary(),
@@ -548,7 +549,7 @@ def run_workload(name: str, args, steps: int, warmup: int, main: bool, reuse=Non
     eng.close()
     del d_img, d_out, h_img, h_out
     torch.cuda.empty_cache()
-    ctx = dict(model_name=model_name, model=model, gain=gain, prec=prec, mask=mask, auto=auto) if rank == 0 else None
+    ctx = dict(model_name=model_name, model=model, gain=gain, prec=prec, terms=terms, auto=auto) if rank == 0 else None
     return out, ctx, img
 
 
@@ -557,6 +558,7 @@ def compact(o):
     return {"workload": o["config"]["workload"], "model": o["config"]["model"], "weights": o["config"]["weights"],
             "H": o["config"]["H"], "W": o["config"]["W"], "tiles": o["config"]["tiles"], "n_gpus": o["n_gpus"], "steps": o["steps"],
             "precision": o["config"]["precision"], "single_mma_layers": o["config"]["single_mma_layers"],
+            "partial_split_layers": o["config"]["partial_split_layers"],
             "value": o["value"], "unit": "MP/s", "ms_per_step": o["ms_per_step"], "value_raw_px": o.get("value_raw_px"),
             "e2e": o["e2e"], "roofline": {"kernel": r["kernel"], "bound": r["bound"], "frac": r["frac"], "step": r["step"]},
             "parity": {k: o["parity"][k] for k in ("max_abs_dp", "argmax_agreement", "max_abs_logit", "within_contract")},

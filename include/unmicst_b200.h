@@ -140,6 +140,18 @@ int umx_device_free_mem(int device, int64_t* free_bytes, int64_t* total_bytes);
 int umx_create(const umx_model_desc* desc, const umx_tensor* weights, int32_t n_weights,
                int32_t device, umx_handle** out);
 
+/* umx_create with the arithmetic chosen per op and per concat source: op_terms[i] (i = op index in plan order, the entry
+ * order of umx_profile_read / umx_describe_plan) = t0 | t1 << 2, where t0 / t1 say which hi/lo correction terms the op
+ * adds to a_hi*w_hi for its first / second source: bit 0 = a_hi*w_lo (weight rounding), bit 1 = a_lo*w_hi (activation
+ * rounding); 15 = the full split, 0 = one MMA per product, -1 = whatever desc->precision implies.  Buffers and weights
+ * get a lo plane only where a term reads it.  This is what the Python layer's `auto` calibration produces. */
+int umx_create_ex(const umx_model_desc* desc, const umx_tensor* weights, int32_t n_weights, int32_t device,
+                  const int32_t* op_terms, int32_t n_op_terms, umx_handle** out);
+
+/* Calibration aid: on a handle built with UMX_PREC_SPLIT3 (every lo plane exists) switch the correction terms of one op
+ * (same encoding) for the following calls; the results equal those of a handle built with umx_create_ex for these terms. */
+int umx_set_op_terms(umx_handle* h, int32_t op_index, int32_t terms);
+
 /* UNet2D.singleImageInferenceCleanup (UnMicst1-5.py:684-685). */
 void umx_destroy(umx_handle* h);
 

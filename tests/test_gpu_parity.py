@@ -108,7 +108,7 @@ def test_legacy_auto_rejects_plain_single(sample_raw, nuclei_model):
     assert rep["chosen"] in ("mixed", "split3")
     assert rep["single_vs_split3_max_abs_dp"] > rep["tolerance"]
     if rep["chosen"] == "mixed":
-        assert rep["single_layers"] and rep["mixed_vs_split3_max_abs_dp"] <= rep["tolerance"]
+        assert (rep["single_layers"] or rep["partial_layers"]) and rep["mixed_vs_split3_max_abs_dp"] <= rep["tolerance"]
     _check_probs(got, _oracle_fw(nuclei_model)(tiles))
 
 
@@ -131,10 +131,41 @@ def test_auto_on_steep_weights_and_image_tiles(sample_raw):
         assert e.precision == rep["chosen"]
     assert rep["probe_tiles"] == len(tiles) and rep["budget"] == AUTO_TOLERANCE
     if rep["chosen"] == "mixed":
-        assert rep["single_layers"] and rep["mixed_vs_split3_max_abs_dp"] <= AUTO_TOLERANCE
-        assert all(l["dp_alone"] >= 0 and l["split_ms"] > 0 for l in rep["layers"])
+        assert (rep["single_layers"] or rep["partial_layers"]) and rep["mixed_vs_split3_max_abs_dp"] <= AUTO_TOLERANCE
+        assert all(min(l["dp"].values()) >= 0 and l["split_ms"] > 0 for l in rep["layers"])
+        assert rep["mixed_vs_split3_max_abs_dp"] <= 1.3 * rep["predicted_quadrature_dp"] + 1e-4      # quadrature model holds
     _check_probs(got, want)
     _check_probs(got_unseen, _oracle_fw(m)(unseen))
+
+
+def test_per_source_correction_terms_v2():
+    """umx_create_ex: which hi/lo correction terms each op adds, per concat source.  Terms 15 everywhere == split3 and
+    0 everywhere == single, bit for bit; a handle built with a partial assignment equals the live split handle switched
+    to the same terms (umx_set_op_terms, what calibration measures) bit for bit; everything stays within the contract."""
+    from unmicst_b200.engine import tensor_ops
+    m = modelzoo.synthetic_model("nucleiDAPI1-5", seed=0)
+    rng = np.random.default_rng(31)
+    tiles = rng.normal(size=(6, 64, 64, 1)).astype(np.float32)
+    want = _oracle_fw(m)(tiles)
+    ops = [i for i, _ in tensor_ops(m)]
+    with _engine(m, precision="split3") as e:
+        split = e.forward_tiles(tiles)
+    with _engine(m, precision="single") as e:
+        single = e.forward_tiles(tiles)
+    with _engine(m, precision="mixed", op_terms={i: 15 for i in ops}) as e:
+        assert np.array_equal(e.forward_tiles(tiles), split)
+    with _engine(m, precision="mixed", op_terms={i: 0 for i in ops}) as e:
+        assert np.array_equal(e.forward_tiles(tiles), single)
+    partial = {i: t for i, t in zip(ops, [2 | 2 << 2, 0, 0, 0, 0, 3 | 0 << 2, 2 | 2 << 2, 2 | 1 << 2, 1 | 1 << 2, 3 | 0 << 2, 2 | 2 << 2, 3 | 2 << 2])}
+    with _engine(m, precision="mixed", op_terms=partial) as e:
+        built = e.forward_tiles(tiles)
+    with _engine(m, precision="split3") as e:
+        for i, t in partial.items():
+            e.set_op_terms(i, t)
+        live = e.forward_tiles(tiles)
+    assert np.array_equal(built, live)
+    _check_probs(built, want)
+    assert not np.array_equal(built, split) and not np.array_equal(built, single)
 
 
 def test_mixed_precision_masks_v2():

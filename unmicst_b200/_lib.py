@@ -62,6 +62,9 @@ SYMBOLS = {
     "umx_device_count": (C.c_int, []),
     "umx_device_free_mem": (C.c_int, [C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "umx_create": (C.c_int, [C.POINTER(umx_model_desc), C.POINTER(umx_tensor), C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "umx_create_ex": (C.c_int, [C.POINTER(umx_model_desc), C.POINTER(umx_tensor), C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32,
+                                C.POINTER(C.c_void_p)]),
+    "umx_set_op_terms": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "umx_destroy": (None, [C.c_void_p]),
     "umx_forward_tiles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
     "umx_infer_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64,

@@ -64,23 +64,36 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
         : "=r"(ok) : "r"(bar), "r"(parity), "r"(ns) : "memory");
     return ok != 0;
 }
-// A pipeline bug must end in a trap, not in a hung GPU: a wait gives up after kSpinLimit failed polls.  Every poll
-// sleeps in hardware for up to the hint, so the limit is reached after 50 ms (polls returning at once) to 100 s
-// (polls sleeping the full hint); no legitimate wait of these kernels lasts a millisecond.
-// (A %globaltimer-based timeout behind a __noinline__ handler measured 3-4 % slower end to end: kept simple.)
-constexpr uint32_t kSpinLimit = 1u << 20;
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+// A pipeline bug must end in a trap, not in a hung GPU - but a wait that is merely slow (compute-sanitizer, a debugger,
+// time-sliced sharing, a clock collapse) must not poison the context: the limit is ELAPSED TIME (20 s on %globaltimer,
+// read once per 1024 failed polls, so the hot path - a wait that succeeds within a few polls - never touches it).
+constexpr unsigned long long kWaitLimitNs = 20ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __noinline__ void mbar_timed_out(uint32_t bar, uint32_t parity) {
+    // one line per stuck role is enough to read the pipeline state: warp 0 = TMA producer, warp 1 = MMA issuer, 2.. = epilogue
+    if ((threadIdx.x & 31) == 0 || threadIdx.x < 64)
+        printf("umx tc_conv: mbarrier wait exceeded 20 s (block %d warp %d thread %d, barrier at shared 0x%x, parity %u)\n",
+               blockIdx.x, threadIdx.x >> 5, threadIdx.x, bar, parity);
+    __trap();
+}
+template <uint32_t HINT_NS>
+__device__ __forceinline__ void mbar_wait_impl(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
-    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
-        if (++spins > kSpinLimit) { printf("umx tc_conv: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    unsigned long long t0 = 0;
+    while (!mbar_try_wait_hint(bar, parity, HINT_NS)) {
+        if ((++spins & 1023u) == 0) {
+            const unsigned long long now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > kWaitLimitNs) mbar_timed_out(bar, parity);
+        }
     }
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait_hint(bar, parity, 100000u)) {
-        if (++spins > kSpinLimit) { printf("umx tc_conv: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
-    }
-}
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) { mbar_wait_impl<20000u>(bar, parity); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { mbar_wait_impl<100000u>(bar, parity); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -222,9 +235,10 @@ __device__ __forceinline__ void umma_acc(uint32_t tmem_d, uint32_t a_lo, uint32_
 
 // The nk <= 4 MMAs (one per 16 channels) of a 64-channel slab; in split mode each product is hi*hi + hi*lo + lo*hi.
 // Only the very first MMA of a work item carries a run-time accumulate flag.
+// `terms` (split layers): bit 0 = the a_hi * w_lo correction, bit 1 = the a_lo * w_hi correction (3 = full hi/lo split)
 template <bool PAIR>
 __device__ __forceinline__ void umma_slab(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
-                                          int nk, bool split, uint32_t a_plane16, uint32_t b_plane16, uint32_t& accumulate, int exp = 0) {
+                                          int nk, bool split, int terms, uint32_t a_plane16, uint32_t b_plane16, uint32_t& accumulate, int exp = 0) {
     if (exp & 128) return;                       // timing experiment: the issue loop without the MMAs
     umma_issue<PAIR>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
     accumulate = 1;
@@ -233,14 +247,14 @@ __device__ __forceinline__ void umma_slab(uint32_t tmem_d, uint32_t a_lo, uint32
         for (int k = 1; k < 4; ++k)
             if (k < nk) umma_acc<PAIR>(tmem_d, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc);
     } else {
-        umma_acc<PAIR>(tmem_d, a_lo, a_hi, b_lo + b_plane16, b_hi, idesc);
-        umma_acc<PAIR>(tmem_d, a_lo + a_plane16, a_hi, b_lo, b_hi, idesc);
+        if (terms & 1) umma_acc<PAIR>(tmem_d, a_lo, a_hi, b_lo + b_plane16, b_hi, idesc);
+        if (terms & 2) umma_acc<PAIR>(tmem_d, a_lo + a_plane16, a_hi, b_lo, b_hi, idesc);
 #pragma unroll
         for (int k = 1; k < 4; ++k)
             if (k < nk) {
                 umma_acc<PAIR>(tmem_d, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc);
-                umma_acc<PAIR>(tmem_d, a_lo + 2 * k, a_hi, b_lo + b_plane16 + 2 * k, b_hi, idesc);
-                umma_acc<PAIR>(tmem_d, a_lo + a_plane16 + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc);
+                if (terms & 1) umma_acc<PAIR>(tmem_d, a_lo + 2 * k, a_hi, b_lo + b_plane16 + 2 * k, b_hi, idesc);
+                if (terms & 2) umma_acc<PAIR>(tmem_d, a_lo + a_plane16 + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc);
             }
     }
 }
@@ -248,38 +262,46 @@ __device__ __forceinline__ void umma_slab(uint32_t tmem_d, uint32_t a_lo, uint32
 // Halo mode: the `ng` taps of one weight slot against one patch, as straight-line code for a compile-time number of
 // 16-channel steps (the gap between two MMAs of the single issuing thread must stay below the ~40-50 cycles one
 // N = 80 MMA takes, or the tensor pipe idles at every tap boundary).
-template <bool PAIR, int NK, bool SPLIT>
+// TERMS (split layers): bit 0 = the a_hi * w_lo correction, bit 1 = the a_lo * w_hi correction; 0 = one MMA per product
+template <bool PAIR, int NK, int TERMS>
 __device__ __forceinline__ void halo_taps(int ng, uint32_t tmem_d, uint32_t& a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                           uint32_t idesc, uint32_t a_plane16, uint32_t bp16, uint32_t b16, int sx, int row_back,
                                           int nx, int& ix, uint32_t& accumulate) {
     for (int j = 0; j < ng; ++j, b_lo += b16) {
         umma_issue<PAIR>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
         accumulate = 1;
-        if (SPLIT) {
-            umma_acc<PAIR>(tmem_d, a_lo, a_hi, b_lo + bp16, b_hi, idesc);
-            umma_acc<PAIR>(tmem_d, a_lo + a_plane16, a_hi, b_lo, b_hi, idesc);
-        }
+        if (TERMS & 1) umma_acc<PAIR>(tmem_d, a_lo, a_hi, b_lo + bp16, b_hi, idesc);
+        if (TERMS & 2) umma_acc<PAIR>(tmem_d, a_lo + a_plane16, a_hi, b_lo, b_hi, idesc);
 #pragma unroll
         for (int k = 1; k < NK; ++k) {
             umma_acc<PAIR>(tmem_d, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc);
-            if (SPLIT) {
-                umma_acc<PAIR>(tmem_d, a_lo + 2 * k, a_hi, b_lo + bp16 + 2 * k, b_hi, idesc);
-                umma_acc<PAIR>(tmem_d, a_lo + a_plane16 + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc);
-            }
+            if (TERMS & 1) umma_acc<PAIR>(tmem_d, a_lo + 2 * k, a_hi, b_lo + bp16 + 2 * k, b_hi, idesc);
+            if (TERMS & 2) umma_acc<PAIR>(tmem_d, a_lo + a_plane16 + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc);
         }
         a_lo += sx;
         if (++ix == nx) { ix = 0; a_lo += row_back; }
     }
 }
 
-template <bool PAIR, bool SPLIT>
+template <bool PAIR, int TERMS>
 __device__ __forceinline__ void halo_taps_nk(int nk, int ng, uint32_t tmem_d, uint32_t& a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                              uint32_t idesc, uint32_t a_plane16, uint32_t bp16, uint32_t b16, int sx, int row_back,
                                              int nx, int& ix, uint32_t& accumulate) {
-    if (nk == 4) halo_taps<PAIR, 4, SPLIT>(ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
-    else if (nk == 1) halo_taps<PAIR, 1, SPLIT>(ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
-    else if (nk == 2) halo_taps<PAIR, 2, SPLIT>(ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
-    else halo_taps<PAIR, 3, SPLIT>(ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
+    if (nk == 4) halo_taps<PAIR, 4, TERMS>(ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
+    else if (nk == 1) halo_taps<PAIR, 1, TERMS>(ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
+    else if (nk == 2) halo_taps<PAIR, 2, TERMS>(ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
+    else halo_taps<PAIR, 3, TERMS>(ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
+}
+
+// per-slab dispatch on the correction terms of the slab's source (uniform in the single issuing thread)
+template <bool PAIR>
+__device__ __forceinline__ void halo_taps_terms(int terms, int nk, int ng, uint32_t tmem_d, uint32_t& a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                uint32_t idesc, uint32_t a_plane16, uint32_t bp16, uint32_t b16, int sx, int row_back,
+                                                int nx, int& ix, uint32_t& accumulate) {
+    if (terms == 3) halo_taps_nk<PAIR, 3>(nk, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
+    else if (terms == 0) halo_taps_nk<PAIR, 0>(nk, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
+    else if (terms == 1) halo_taps_nk<PAIR, 1>(nk, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
+    else halo_taps_nk<PAIR, 2>(nk, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
 }
 
 // Everything the epilogue of one accumulator tile needs that does not change from item to item.
@@ -411,12 +433,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     // Plain mode: one ring of `stages` slots, each [A tile planes][B tile planes] for one (tap, 64-channel slab).
     // Halo mode (high-resolution layers): ring A holds one (bh+halo) x (bw+halo) pixel patch per slab that serves
     // every tap (A is fetched from L2 once instead of once per tap); ring B holds the weights of `gb` taps per slot.
-    const int planes = p.planes;
+    // operand planes held per slot: A (activations) hi [+ lo when some source uses the a_lo * w_hi term], B (weights)
+    // hi [+ lo when some source uses the a_hi * w_lo term]
+    const int planes_a = p.planes_a, planes_b = p.planes_b;
     const int a_box_bytes = HALO ? p.bn * p.ph * p.pw * 128 : kAPlaneBytes;    // bytes one TMA box delivers per plane
     const int a_plane_bytes = HALO ? ((a_box_bytes + 1023) & ~1023) : kAPlaneBytes;
-    const int a_bytes = planes * a_plane_bytes;
+    const int a_bytes = planes_a * a_plane_bytes;
     const int b_plane_bytes = (PAIR ? p.n_t / 2 : p.n_t) * 128;     // pair mode: each CTA stages half of the N rows
-    const int b_bytes = planes * b_plane_bytes;
+    const int b_bytes = planes_b * b_plane_bytes;
     const int ks = HALO ? 1 : p.kslab;                               // plain mode: 64-channel slabs per ring slot
     const int slab_bytes = a_bytes + b_bytes;
     const int stage_bytes = HALO ? a_bytes : ks * slab_bytes;
@@ -479,6 +503,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (PAIR) cluster_sync_all();       // peer barriers are initialised before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if ((p.exp_flags & 2048) && blockIdx.x == 0 && threadIdx.x == 0)
+        printf("umx tc_conv layout: full0 0x%x empty0 0x%x fullB0 0x%x emptyB0 0x%x tfull0 0x%x tempty0 0x%x stages %d/%d gb %d\n",
+               full0, empty0, fullB0, emptyB0, tfull0, tempty0, n_stages, nb_stages, gb);
 
     const int m_tiles = (p.bn > 1) ? (p.n_tiles + p.bn - 1) / p.bn : p.n_tiles * (p.in_w / p.bw) * (p.in_h / p.bh);
     const int per_unit = PAIR ? 2 : 1;
@@ -499,7 +526,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             if constexpr (HALO) {
                 const int hx0 = p.hx0, hy0 = p.hy0, n_chunks = nch0 + nch1;
                 const bool nh = p.halo_nh != 0;
-                const uint32_t txA = (PAIR ? 2u : 1u) * (uint32_t)(planes * a_box_bytes);
+                const uint32_t txA1 = (PAIR ? 2u : 1u) * (uint32_t)a_box_bytes;      // per plane; a source loads its lo plane only when its a_lo term is on
                 int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
                 unsigned long long c_wa = 0, c_wb = 0, c_work = 0; DbgClock clk; clk.start(dbg_on);
                 const uint32_t txB = (PAIR ? 2u : 1u) * (uint32_t)(gb * b_bytes);      // a weight box always carries gb taps
@@ -516,10 +543,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     clk.lap(c_wa);
                     const uint32_t fa = full0 + 8 * sa;
                     const uint32_t da = smem_u32(smem) + (uint32_t)(sa * stage_bytes);
+                    const int npl = (((second ? p.terms1 : p.terms0) & 2) && planes_a == 2) ? 2 : 1;
                     if (noload) { if (leader) mbar_arrive(fa); }
-                    else if (leader) mbar_expect_tx(fa, txA);
+                    else if (leader) mbar_expect_tx(fa, txA1 * (uint32_t)npl);
                     const int c2 = nh ? ta.n0 : ta.y0 - hy0, c3 = nh ? ta.y0 - hy0 : ta.n0;     // {C, W, tiles, H} order on 8x8 grids
-                    for (int pl = 0; pl < planes && !noload; ++pl) {
+                    for (int pl = 0; pl < npl && !noload; ++pl) {
                         if (PAIR) tma_load_5d_pair(da + pl * a_plane_bytes, mapA, fa, cc, ta.x0 - hx0, c2, c3, pl);
                         else tma_load_5d(da + pl * a_plane_bytes, mapA, fa, cc, ta.x0 - hx0, c2, c3, pl);
                     }
@@ -635,7 +663,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if (leader && elect_one()) {
             // ================= MMA issuer (leader CTA only in pair mode) =================
             const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_t >> 3) << 17) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
-            const bool split = planes == 2;
+            const int terms0 = p.terms0, terms1 = p.terms1;
+            const bool split = (terms0 | terms1) != 0;
             const uint32_t a_plane16 = (uint32_t)a_plane_bytes >> 4, b_plane16 = (uint32_t)b_plane_bytes >> 4;
             const uint32_t b_hi = desc_hi(1024);
             const bool a1c = p.a1_center != 0; const int ctap = p.center_tap;
@@ -682,8 +711,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             const uint32_t r_off = (uint32_t)((second && a1c ? nch0 * gb + (cb - nch0) : cb * gb) * b_bytes);
                             const uint32_t b_lo = desc_lo(smem_u32(smem_b) + r_off) + (centre_only ? 0u : (uint32_t)g.wi0 * b16);
                             if (exp_mma & 128) {}
-                            else if (split) halo_taps_nk<PAIR, true>(nk, te, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, g.nx, ix, accumulate);
-                            else halo_taps_nk<PAIR, false>(nk, te, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, g.nx, ix, accumulate);
+                            else halo_taps_terms<PAIR>(split ? (second ? terms1 : terms0) : 0, nk, te, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, g.nx, ix, accumulate);
                         } else
                         for (int t0 = 0; t0 < te; t0 += gb) {
                             const int ng = min(gb, te - t0);
@@ -693,8 +721,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             tc_fence_after();
                             const uint32_t b_lo = desc_lo(smem_u32(smem_b) + (uint32_t)(sb * gb * b_bytes));
                             if (exp_mma & 128) {}                 // timing experiment: the issue loop without the MMAs
-                            else if (split) halo_taps_nk<PAIR, true>(nk, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, g.nx, ix, accumulate);
-                            else halo_taps_nk<PAIR, false>(nk, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, g.nx, ix, accumulate);
+                            else halo_taps_terms<PAIR>(split ? (second ? terms1 : terms0) : 0, nk, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, g.nx, ix, accumulate);
                             if (PAIR) umma_commit_pair(emptyB0 + 8 * sb); else umma_commit(emptyB0 + 8 * sb);
                             if (++sb == nb_stages) { sb = 0; pb ^= 1; }
                         }
@@ -728,7 +755,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             for (int j = 0; j < ns; ++j, a_lo += slab16) {
                                 const int cb = c0 + j;
                                 const int nk = one_mma ? 1 : (cb == nch0 - 1 ? nk_last0 : (cb == nch0 + nch1 - 1 ? nk_last1 : 4));
-                                umma_slab<PAIR>(tmem_d, a_lo, a_hi, a_lo + ab16, b_hi, idesc, nk, split, a_plane16, b_plane16, accumulate, exp_mma);
+                                umma_slab<PAIR>(tmem_d, a_lo, a_hi, a_lo + ab16, b_hi, idesc, nk, split, cb >= nch0 ? terms1 : terms0, a_plane16, b_plane16, accumulate, exp_mma);
                             }
                             // frees the smem slot (in both CTAs) when these MMAs retire
                             if (PAIR) umma_commit_pair(empty0 + 8 * stage); else umma_commit(empty0 + 8 * stage);
@@ -888,9 +915,9 @@ size_t tc_conv_fixed_bytes(const TcConvParams& p) {
 }
 size_t tc_conv_a_bytes(const TcConvParams& p) {
     const size_t box = p.halo ? (((size_t)p.bn * p.ph * p.pw * 128 + 1023) & ~(size_t)1023) : (size_t)kAPlaneBytes;
-    return (size_t)p.planes * box;
+    return (size_t)p.planes_a * box;
 }
-size_t tc_conv_b_bytes(const TcConvParams& p) { return (size_t)p.planes * (size_t)(p.pair ? p.n_t / 2 : p.n_t) * 128; }
+size_t tc_conv_b_bytes(const TcConvParams& p) { return (size_t)p.planes_b * (size_t)(p.pair ? p.n_t / 2 : p.n_t) * 128; }
 size_t tc_conv_smem_bytes(const TcConvParams& p) {
     if (p.halo) return p.stages * tc_conv_a_bytes(p) + (p.b_resident ? (size_t)p.b_res_bytes : (size_t)p.b_stages * p.gb * tc_conv_b_bytes(p)) + tc_conv_fixed_bytes(p);
     return p.stages * (size_t)(p.kslab > 0 ? p.kslab : 1) * (tc_conv_a_bytes(p) + tc_conv_b_bytes(p)) + tc_conv_fixed_bytes(p);

@@ -317,15 +317,17 @@ int build_plan(umx_handle* h) {
 
 enum { TC_NONE = 0, TC_PLAIN = 1, TC_SHORT_SKIP = 3, TC_SHORT_A1 = 4 };
 
-// fp16 operand planes of a tensor-path op: 1 = one MMA per product, 2 = hi/lo split (three MMAs)
-int op_planes(const umx_handle* h, const Op& op) {
-    if (h->precision == UMX_PREC_SINGLE) return 1;
-    if (h->precision == UMX_PREC_MIXED) {
-        const size_t idx = (size_t)(&op - h->ops.data());
-        return (idx < 64 && ((h->single_mask >> idx) & 1)) ? 1 : 2;
-    }
-    return 2;
+// hi/lo correction terms of a tensor-path op, per concat source: bit 0 = a_hi * w_lo, bit 1 = a_lo * w_hi.
+// 3 = the full split (three MMAs per product), 0 = one MMA per product; packed t0 | t1 << 2.
+int op_terms(const umx_handle* h, const Op& op) {
+    const size_t idx = (size_t)(&op - h->ops.data());
+    if (idx < h->op_terms.size() && h->op_terms[idx] >= 0) return h->op_terms[idx] & 15;
+    if (h->precision == UMX_PREC_SINGLE) return 0;
+    if (h->precision == UMX_PREC_MIXED) return (idx < 64 && ((h->single_mask >> idx) & 1)) ? 0 : 15;
+    return 15;
 }
+// fp16 operand planes of a tensor-path op: 1 = one MMA per product, 2 = some hi/lo correction term is on
+int op_planes(const umx_handle* h, const Op& op) { return op_terms(h, op) ? 2 : 1; }
 
 // Which tensor-path form (if any) can run this op (after rewrite_narrow_sources).
 //  - one term: k x k conv / conv-transpose of one or two wide concat sources (TC_PLAIN); k = 1 is the tap-expanded
@@ -528,6 +530,23 @@ int lower_conv_tc(umx_handle* h, Op& op) {
         }
     }
     tp.planes = planes;
+    tp.terms0 = op_terms(h, op) & 3; tp.terms1 = (op_terms(h, op) >> 2) & 3;
+    if (!a1) tp.terms1 = tp.terms0;             // single source: one setting
+    tp.planes_a = ((tp.terms0 | tp.terms1) & 2) ? 2 : 1; tp.planes_b = ((tp.terms0 | tp.terms1) & 1) ? 2 : 1;
+    if (const char* e = getenv("UMX_TC_TERMS")) {          // experiment: "name:t0:t1;name:t0:t1" picks the correction terms per source
+        std::string spec(e);
+        size_t pos = 0;
+        while (pos < spec.size()) {
+            const size_t end = std::min(spec.find(';', pos), spec.size());
+            const std::string item = spec.substr(pos, end - pos);
+            const size_t c1 = item.find(':'), c2 = item.find(':', c1 + 1);
+            if (c1 != std::string::npos && c2 != std::string::npos && item.substr(0, c1) == op.name.substr(0, c1) &&
+                (op.name.size() == c1 || op.name[c1] == '+')) {
+                tp.terms0 = atoi(item.substr(c1 + 1, c2 - c1 - 1).c_str()) & 3; tp.terms1 = atoi(item.substr(c2 + 1).c_str()) & 3;
+            }
+            pos = end + 1;
+        }
+    }
     {
         const char* e = getenv("UMX_TC_PAIR");
         tp.pair = (e ? atoi(e) : 1) && ((tp.n_t / 2) % 8 == 0) ? 1 : 0;
@@ -581,12 +600,15 @@ int lower_conv_tc(umx_handle* h, Op& op) {
                 // (the slabs of a 1x1 term exist at the centre tap only: one tile each instead of ntaps_w)
                 const size_t res = ((size_t)nc0 * ntaps_w + (size_t)nc1 * (tp.a1_center ? 1 : ntaps_w)) * bb;
                 const char* e = getenv("UMX_TC_RESIDENT");
-                if ((e ? atoi(e) : 1) && tp.n_ntiles == 1 && ntaps_w <= 9 && planes == 1 && budget >= res + 3 * ab) {
+                if ((e ? atoi(e) : 1) && tp.n_ntiles == 1 && ntaps_w <= 9 && planes == 1 && (tp.terms0 | tp.terms1) == 0 && budget >= res + 3 * ab) {
                     tp.b_resident = 1; tp.gb = ntaps_w; tp.b_stages = n_chunks; tp.b_res_bytes = (int32_t)res;
                     tp.stages = (int)std::min<size_t>(6, (budget - res) / ab);
                 }
             }
-            if (tp.b_stages < 2) { tp.halo = 0; tp.halo_nh = 0; tp.bw = std::min(a0.w, 16); tp.bh = std::min(a0.h, 128 / tp.bw); tp.bn = 128 / (tp.bw * tp.bh); }
+            // the producer runs the patch loads stages-1 slabs ahead of the weight loads of the same slab stream; with only
+            // two patch slots the patch of slab s+1 would queue behind weights that cannot all land before that very
+            // patch is consumed (a weight ring shorter than a slab's taps): a deadlock, so such layers run in plain mode
+            if (tp.b_stages < 2 || (tp.stages < 3 && !tp.b_resident)) { tp.halo = 0; tp.halo_nh = 0; tp.bw = std::min(a0.w, 16); tp.bh = std::min(a0.h, 128 / tp.bw); tp.bn = 128 / (tp.bw * tp.bh); }
         }
         tp.kslab = 1;
         if (!tp.halo) {
@@ -662,21 +684,24 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     for (int i = 0; i < ntaps_w; ++i)
         memcpy(&wperm[(size_t)i * cin * sp.cout], &wmain[(size_t)order[i] * cin * sp.cout], (size_t)cin * sp.cout * sizeof(float));
     for (int i = 0; i < ntaps_w; ++i) if (order[i] == tp.center_tap) { tp.center_tap = i; break; }
+    const int planes_b = tp.planes_b, planes_a = tp.planes_a;
     std::vector<__half> wh;
-    split_weights(wperm, taps_dev, cin, sp.cout, planes, &wh);
+    split_weights(wperm, taps_dev, cin, sp.cout, planes_b, &wh);
     __half* dw = nullptr;
     UMX_CUDA_TRY(cudaMalloc(&dw, wh.size() * sizeof(__half)));
     h->dev_allocs.push_back(reinterpret_cast<float*>(dw));
     UMX_CUDA_TRY(cudaMemcpy(dw, wh.data(), wh.size() * sizeof(__half), cudaMemcpyHostToDevice));
-    int rc = make_weight_tensor_map(&op.mapB, dw, planes, taps_dev, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, planes, box_taps);
+    int rc = make_weight_tensor_map(&op.mapB, dw, planes_b, taps_dev, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, planes_b, box_taps);
     if (rc) { set_error("%s: cuTensorMapEncodeTiled(weights) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
     op.mapB1 = op.mapB;
     if (tp.b_resident && tp.a1_center) {
-        rc = make_weight_tensor_map(&op.mapB1, dw, planes, taps_dev, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, planes, 1);
+        rc = make_weight_tensor_map(&op.mapB1, dw, planes_b, taps_dev, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, planes_b, 1);
         if (rc) { set_error("%s: cuTensorMapEncodeTiled(weights, one tap) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
     }
     if (!a0.dh || (a1 && !a1->dh)) { set_error("%s: fp16 source buffer missing", op.name.c_str()); return UMX_EINVAL; }
-    const int box_w = tp.halo ? tp.pw : tp.bw, box_h = tp.halo ? tp.ph : tp.bh, box_p = tp.halo ? 1 : planes;
+    if (!tp.halo && planes_a == 2 && (a0.planes < 2 || (a1 && a1->planes < 2))) { set_error("%s: plain-mode op needs the lo plane of every source", op.name.c_str()); return UMX_EINVAL; }
+    if (tp.halo && (((tp.terms0 & 2) && a0.planes < 2) || (a1 && (tp.terms1 & 2) && a1->planes < 2))) { set_error("%s: lo plane of a source is missing", op.name.c_str()); return UMX_EINVAL; }
+    const int box_w = tp.halo ? tp.pw : tp.bw, box_h = tp.halo ? tp.ph : tp.bh, box_p = tp.halo ? 1 : planes_a;
     rc = make_act_tensor_map(&op.mapA0, a0.dh, a0.planes, a0.plane_elems, h->cap_tiles, a0.h, a0.w, a0.cs(), box_w, box_h, tp.bn, box_p, tp.halo_nh);
     if (rc) { set_error("%s: cuTensorMapEncodeTiled(A0) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
     if (a1) {
@@ -716,10 +741,22 @@ int lower_plan(umx_handle* h) {
             for (size_t ti = 0; ti < op.spec.terms.size(); ++ti) {
                 const TermHost& t = op.spec.terms[ti];
                 if (op.tc_mode == TC_SHORT_SKIP && ti == 1) { h->bufs[t.src0].need_f = true; continue; }
-                for (int s : {t.src0, t.src1}) {
+                // the lo plane of a buffer exists only where a consumer multiplies it (a_lo * w_hi term of that source);
+                // source 1 of the kernel = the second concat source, or the 1x1 term's buffer (TC_SHORT_A1)
+                const int terms = op_terms(h, op);
+                const bool two_src = t.src1 >= 0 || op.tc_mode == TC_SHORT_A1;
+                const int si[2] = {t.src0, t.src1};
+                for (int j = 0; j < 2; ++j) {
+                    const int s = si[j];
                     if (s < 0) continue;
-                    if (op.use_tc) { h->bufs[s].need_h = true; if (op_planes(h, op) == 2) h->bufs[s].need_lo = true; }
-                    else h->bufs[s].need_f = true;
+                    if (op.use_tc) {
+                        h->bufs[s].need_h = true;
+                        const int ts = !two_src ? (terms & 3) : ((ti == 1 || j == 1) ? (terms >> 2) & 3 : terms & 3);
+                        // plain (non-halo) mode, i.e. grids below 16 x 16, fetches the planes of both sources with one box shape:
+                        // there any a_lo term asks for the lo plane of every source
+                        const bool any_a_lo = ((terms | (terms >> 2)) & 2) != 0;
+                        if ((ts & 2) || (any_a_lo && h->bufs[t.src0].h < 16)) h->bufs[s].need_lo = true;
+                    } else h->bufs[s].need_f = true;
                 }
             }
         } else if (op.kind == OP_TAPS) {
@@ -926,6 +963,24 @@ void* umx_host_alloc(int64_t bytes) {
 void umx_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int umx_create(const umx_model_desc* desc, const umx_tensor* weights, int32_t n_weights, int32_t device, umx_handle** out) {
+    return umx_create_ex(desc, weights, n_weights, device, nullptr, 0, out);
+}
+
+int umx_set_op_terms(umx_handle* h, int32_t op_index, int32_t terms) {
+    if (!h || op_index < 0 || op_index >= (int)h->ops.size() || terms < 0 || terms > 15) { set_error("umx_set_op_terms: bad argument"); return UMX_EINVAL; }
+    Op& op = h->ops[op_index];
+    if (op.kind != OP_CONV || !op.use_tc) { set_error("op %d is not on the tensor path", op_index); return UMX_EINVAL; }
+    TcConvParams& tp = op.tcp;
+    if (tp.planes_a != 2 || tp.planes_b != 2 || !h->full_split) { set_error("op %d was not built with the full hi/lo split: its lo planes do not exist", op_index); return UMX_EINVAL; }
+    // every plane the full split needs exists (buffers, weights, shared-memory slots), so any subset of the terms can
+    // be switched on this live handle; the slot layout stays that of the full split (a calibration aid: the arithmetic
+    // equals that of a handle built with these terms, the loads are those of the full split)
+    tp.terms0 = terms & 3; tp.terms1 = tp.c1 > 0 ? (terms >> 2) & 3 : tp.terms0;
+    return UMX_OK;
+}
+
+int umx_create_ex(const umx_model_desc* desc, const umx_tensor* weights, int32_t n_weights, int32_t device,
+                  const int32_t* op_terms_in, int32_t n_op_terms, umx_handle** out) {
     if (!desc || !out || (!weights && n_weights > 0)) { set_error("umx_create: null argument"); return UMX_EINVAL; }
     *out = nullptr;
     if (desc->abi_version != UMX_ABI_VERSION) { set_error("umx_create: ABI version %d != %d", desc->abi_version, UMX_ABI_VERSION); return UMX_EINVAL; }
@@ -973,6 +1028,11 @@ int umx_create(const umx_model_desc* desc, const umx_tensor* weights, int32_t n_
     if (h->precision < UMX_PREC_FP32 || h->precision > UMX_PREC_MIXED) { set_error("unknown precision %d", desc->precision); umx_destroy(h); return UMX_EINVAL; }
     rc = rewrite_narrow_sources(h);
     if (rc != UMX_OK) { umx_destroy(h); return rc; }
+    h->full_split = h->precision == UMX_PREC_SPLIT3 && !op_terms_in;
+    if (op_terms_in && h->precision != UMX_PREC_FP32) {
+        h->op_terms.assign(h->ops.size(), -1);
+        for (int i = 0; i < n_op_terms && i < (int)h->ops.size(); ++i) h->op_terms[i] = op_terms_in[i] < 0 ? -1 : (int8_t)(op_terms_in[i] & 15);
+    }
     int64_t per_tile = 0;
     for (auto& b : h->bufs) per_tile += b.per_tile() * 4;
     per_tile += (int64_t)S * S * h->K * 4;

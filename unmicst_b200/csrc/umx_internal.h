@@ -118,6 +118,8 @@ struct umx_handle {
     int num_sms = 148;
     int precision = UMX_PREC_SPLIT3;
     uint64_t single_mask = 0;                    // UMX_PREC_MIXED: ops (by index) that run with one MMA per product
+    bool full_split = false;                     // every tensor-path op carries both planes of everything (umx_set_op_terms allowed)
+    std::vector<int8_t> op_terms;                // umx_create_ex: per op, t0 | t1 << 2 (-1: what the precision implies)
     std::vector<int> chan;                       // nOutX
     std::map<std::string, umx::HostTensor> tensors;
     std::vector<float*> dev_allocs;              // weights etc.

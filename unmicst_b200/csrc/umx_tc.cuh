@@ -24,7 +24,9 @@ struct TcConvParams {
     int32_t n_ntiles;            // ceil(cout / n_t)
     int32_t nphase, os;          // conv: 1,1   conv-transpose: 4,2
     TcPhaseGrid grid[4];         // per phase tap grid (conv 3x3/5x5: 1 phase; conv-transpose: 4 phases, <= 9 taps)
-    int32_t planes;              // 1: fp16 operands, 1 MMA/product; 2: hi/lo split, 3 MMAs/product
+    int32_t planes;              // 1: fp16 operands, 1 MMA/product; 2: hi/lo split, up to 3 MMAs/product
+    int32_t planes_a, planes_b;  // planes a slot holds (layout): A hi [+ lo], B hi [+ lo]; fixed when the op is lowered
+    int32_t terms0, terms1;      // split layers, per concat source: bit 0 = a_hi*w_lo correction, bit 1 = a_lo*w_hi correction (3 = full split)
     int32_t stages;              // smem pipeline depth (halo mode: patch slots)
     int32_t halo;                // 1: one (bh+halo) x (bw+halo) pixel patch per 64-channel slab serves every tap
     int32_t pw, ph, hx0, hy0;    // patch size and left/top halo (halo mode)

@@ -194,45 +194,6 @@ def sample_probe_tiles(image: np.ndarray, S: int, C: int, mean: float, std: floa
     return out
 
 
-def tensor_ops(model: Model) -> List[Tuple[int, str]]:
-    """(op index, name) of every op the tensor path runs in the split plan: the candidates of UMX_PREC_MIXED."""
-    out = []
-    for line in describe_plan(model, "split3"):
-        f = line.split()
-        if len(f) > 3 and f[1] == "conv" and f[3] == "tensor":
-            out.append((int(f[0]), f[2]))
-    return out
-
-
-def choose_single_mask(errs: Dict[int, float], costs: Dict[int, float], budget: float, exclude: Sequence[int] = ()) -> int:
-    """Error-budgeted layer selection: the subset of ops to run with one MMA per product that saves the most time
-    while the predicted max|dp| — the per-layer contributions added in quadrature (rounding errors of different layers
-    are independent) — stays inside ``budget``.  Exact over all subsets up to 20 candidates, ratio-greedy beyond."""
-    ops = [i for i in errs if i not in exclude and costs.get(i, 0.0) > 0.0]
-    if not ops:
-        return 0
-    b2 = budget * budget
-    if len(ops) <= 20:
-        best_mask, best_gain = 0, 0.0
-        e2 = [errs[i] ** 2 for i in ops]
-        cs = [costs[i] for i in ops]
-        for sub in range(1, 1 << len(ops)):
-            e, g = 0.0, 0.0
-            for k in range(len(ops)):
-                if sub >> k & 1:
-                    e += e2[k]
-                    g += cs[k]
-            if e <= b2 and g > best_gain:
-                best_gain, best_mask = g, sub
-        return sum(1 << ops[k] for k in range(len(ops)) if best_mask >> k & 1)
-    mask, e = 0, 0.0
-    for i in sorted(ops, key=lambda i: errs[i] ** 2 / costs[i]):
-        if e + errs[i] ** 2 <= b2:
-            e += errs[i] ** 2
-            mask |= 1 << i
-    return mask
-
-
 def mask_to_reserved(mask: int) -> Tuple[int, int]:
     """64-bit op mask of UMX_PREC_MIXED -> the two int32 fields umx_model_desc.reserved[0] (low word) and [1] (high
     word) carry it in: same bit patterns, expressed as signed 32-bit values for ctypes."""
@@ -273,16 +234,111 @@ def describe_plan(model: Model, precision: str = "default", single_mask: int = 0
     return buf.value.decode().splitlines()
 
 
-def calibrate(model: Model, device: int = 0, probe_tiles: Optional[np.ndarray] = None, budget: float = AUTO_TOLERANCE,
-              verbose: bool = False) -> Tuple[str, int, Dict]:
-    """Pick the cheapest arithmetic that keeps max|dp| vs the hi/lo split within ``budget`` on ``probe_tiles``
-    (tiles of the image about to be processed: sample_probe_tiles).  Returns (precision, single_mask, report).
+def tensor_ops(model: Model) -> List[Tuple[int, str]]:
+    """(op index, name) of every op the tensor path runs in the split plan: the candidates of per-layer precision."""
+    return [(i, n) for i, n, _ in tensor_op_sources(model)]
 
-    1. all-single within budget -> 'single'.
-    2. otherwise measure, once per tensor-path layer, the max|dp| that running only this layer with one MMA per product
-       causes (its error contribution) and the time it saves (profiled single vs split pass), choose the subset with
-       the largest saving whose contributions, added in quadrature, fit 80 % of the budget (choose_single_mask), then
-       verify the chosen mask as a whole and drop the least profitable layers until the measured error fits.
+
+def tensor_op_sources(model: Model) -> List[Tuple[int, str, List[float]]]:
+    """(op index, name, [K of source 0, K of source 1]) per tensor-path op, K = taps x channels the source contributes to
+    the contraction (the cost weight of its correction terms).  Parsed from the host-only plan description."""
+    out = []
+    for line in describe_plan(model, "split3"):
+        f = line.split()
+        if len(f) > 3 and f[1] == "conv" and f[3] == "tensor":
+            terms = line.split("terms=")[1].replace("]", "").split("[")[1:]
+            ks: List[float] = []
+            for t in terms:                                   # "k=3 a:80|b:160"  or  "k=3 up:80" + "k=1 taps:9"
+                parts = t.split()
+                k = int(parts[0][2:])
+                for srcs in parts[1].split("|"):
+                    ks.append(float(k * k * int(srcs.rsplit(":", 1)[1])))
+            if "mode=3" in f:                                 # the second term is the fp32 one-channel shortcut of the epilogue
+                ks = ks[:1]
+            out.append((int(f[0]), f[2], ks[:2]))
+    return out
+
+
+def choose_single_mask(errs: Dict[int, float], costs: Dict[int, float], budget: float, exclude: Sequence[int] = ()) -> int:
+    """Error-budgeted layer selection (binary form): the subset of ops to run with one MMA per product that saves the
+    most time while the predicted max|dp| — the per-layer contributions added in quadrature (rounding errors of
+    different layers are independent) — stays inside ``budget``.  Exact over all subsets up to 20 candidates."""
+    ops = [i for i in errs if i not in exclude and costs.get(i, 0.0) > 0.0]
+    if not ops:
+        return 0
+    b2 = budget * budget
+    if len(ops) <= 20:
+        best_mask, best_gain = 0, 0.0
+        e2 = [errs[i] ** 2 for i in ops]
+        cs = [costs[i] for i in ops]
+        for sub in range(1, 1 << len(ops)):
+            e, g = 0.0, 0.0
+            for k in range(len(ops)):
+                if sub >> k & 1:
+                    e += e2[k]
+                    g += cs[k]
+            if e <= b2 and g > best_gain:
+                best_gain, best_mask = g, sub
+        return sum(1 << ops[k] for k in range(len(ops)) if best_mask >> k & 1)
+    mask, e = 0, 0.0
+    for i in sorted(ops, key=lambda i: errs[i] ** 2 / costs[i]):
+        if e + errs[i] ** 2 <= b2:
+            e += errs[i] ** 2
+            mask |= 1 << i
+    return mask
+
+
+def choose_op_terms(options: Dict[int, List[Tuple[int, float, float]]], budget: float, bins: int = 2000) -> Dict[int, int]:
+    """Multiple-choice knapsack behind `auto`: ``options[op]`` lists (terms, max|dp| when only this op runs with these
+    terms, time); pick one option per op minimising the total time while the contributions, added in quadrature, stay
+    inside ``budget``.  Dynamic programme over the squared-error budget in ``bins`` steps (errors rounded UP to a bin,
+    so the answer is feasible; every op must offer an option with zero error: the full split)."""
+    b2 = budget * budget
+    step = b2 / bins
+    INF = float("inf")
+    best = [0.0] * (bins + 1)             # best[j]: least time with squared error <= j * step, over the ops seen so far
+    choice: List[List[int]] = []
+    ops = sorted(options)
+    table = [best]
+    for op in ops:
+        prev = table[-1]
+        cur = [INF] * (bins + 1)
+        pick = [-1] * (bins + 1)
+        for oi, (_, err, t) in enumerate(options[op]):
+            w = 0 if err <= 0 else int(-(-(err * err) // step))
+            if w > bins:
+                continue
+            for j in range(w, bins + 1):
+                v = prev[j - w] + t
+                if v < cur[j]:
+                    cur[j], pick[j] = v, oi
+        table.append(cur)
+        choice.append(pick)
+    if table[-1][bins] == INF:
+        raise ValueError("no feasible precision assignment (every op needs a zero-error option)")
+    out: Dict[int, int] = {}
+    j = bins
+    for k in range(len(ops) - 1, -1, -1):
+        oi = choice[k][j]
+        terms, err, _ = options[ops[k]][oi]
+        out[ops[k]] = terms
+        j -= 0 if err <= 0 else int(-(-(err * err) // step))
+    return out
+
+
+def calibrate(model: Model, device: int = 0, probe_tiles: Optional[np.ndarray] = None, budget: float = AUTO_TOLERANCE,
+              verbose: bool = False) -> Tuple[str, Dict[int, int], Dict]:
+    """Pick the cheapest arithmetic that keeps max|dp| vs the full hi/lo split within ``budget`` on ``probe_tiles``
+    (tiles of the image about to be processed: sample_probe_tiles).  Returns (precision, op_terms, report).
+
+    The full split adds two correction MMAs to every product: a_hi*w_lo (weight rounding, term bit 0) and a_lo*w_hi
+    (activation rounding, bit 1).  They can be switched per layer and per concat source.
+    1. all layers with one MMA per product within budget -> 'single'.
+    2. otherwise, on ONE live split engine (umx_set_op_terms, no rebuilds): for every tensor-path layer and every term
+       combination, the max|dp| this layer alone causes; time per option interpolated between the layer's profiled
+       single and split times by the share of correction MMAs it issues; choose_op_terms picks the fastest assignment
+       whose contributions fit the budget in quadrature; the chosen assignment is then measured as a whole on the same
+       engine and the budget tightened until the measured error fits.
     """
     S, C = int(model.hp["imSize"]), int(model.hp["nChannels"])
     if probe_tiles is None:
@@ -302,47 +358,69 @@ def calibrate(model: Model, device: int = 0, probe_tiles: Optional[np.ndarray] =
         e.profile_enable(False)
         return prof
 
+    with Engine(model, device, "single", batch) as es:
+        got_single = es.forward_tiles(probe_tiles)
+        prof_single = profile_of(es)
+    srcs = [(i, n, ks) for i, n, ks in tensor_op_sources(model)]
     with Engine(model, device, "split3", batch) as ref:
         want = ref.forward_tiles(probe_tiles)
+        d_single = float(np.abs(got_single - want).max())
+        report: Dict = {"probe_tiles": int(len(probe_tiles)), "budget": budget, "tolerance": budget,
+                        "single_vs_split3_max_abs_dp": d_single}
+        if d_single <= budget:
+            report["chosen"] = "single"
+            return "single", {}, report
         prof_split = profile_of(ref)
-
-    def err_of(prec: str, mask: int = 0) -> float:
-        with Engine(model, device, prec, batch, single_mask=mask) as e:
-            return float(np.abs(e.forward_tiles(probe_tiles) - want).max())
-
-    with Engine(model, device, "single", batch) as es:
-        d_single = float(np.abs(es.forward_tiles(probe_tiles) - want).max())
-        prof_single = profile_of(es)
-    report: Dict = {"probe_tiles": int(len(probe_tiles)), "budget": budget, "single_vs_split3_max_abs_dp": d_single,
-                    "tolerance": budget}
-    if d_single <= budget:
-        report["chosen"] = "single"
-        return "single", 0, report
-    cands = [(i, n) for i, n in tensor_ops(model) if i < 64]
-    errs: Dict[int, float] = {}
-    costs: Dict[int, float] = {}
-    layers = []
-    for i, name in cands:
-        errs[i] = err_of("mixed", 1 << i)
-        costs[i] = max(0.0, prof_split[i]["ms"] - prof_single[i]["ms"])
-        layers.append({"op": i, "name": name, "dp_alone": errs[i], "split_ms": round(prof_split[i]["ms"], 4),
-                       "single_ms": round(prof_single[i]["ms"], 4)})
-        if verbose:
-            print(f"[calibrate] {name:14s} dp_alone {errs[i]:.2e}  split {prof_split[i]['ms']:.3f} ms  single {prof_single[i]['ms']:.3f} ms", flush=True)
-    mask = choose_single_mask(errs, costs, 0.8 * budget)
-    d_mixed = err_of("mixed", mask) if mask else 0.0
-    dropped = []
-    while mask and d_mixed > budget:
-        worst = max((i for i in errs if mask >> i & 1), key=lambda i: errs[i] ** 2 / max(costs[i], 1e-9))
-        mask &= ~(1 << worst)
-        dropped.append(worst)
-        d_mixed = err_of("mixed", mask) if mask else 0.0
-    names = dict(cands)
-    report.update({"layers": layers, "single_layers": [names[i] for i in names if mask >> i & 1],
-                   "dropped_after_verify": [names[i] for i in dropped], "mixed_vs_split3_max_abs_dp": d_mixed,
-                   "predicted_quadrature_dp": float(np.sqrt(sum(errs[i] ** 2 for i in errs if mask >> i & 1))),
-                   "single_mask": mask, "chosen": "mixed" if mask else "split3"})
-    return ("mixed" if mask else "split3"), mask, report
+        options: Dict[int, List[Tuple[int, float, float]]] = {}
+        layers = []
+        for i, name, ks in srcs:
+            two = len(ks) > 1
+            k0, k1 = ks[0], (ks[1] if two else 0.0)
+            t_single, t_split = prof_single[i]["ms"], max(prof_split[i]["ms"], prof_single[i]["ms"])
+            opts: List[Tuple[int, float, float]] = []
+            rec = {"op": i, "name": name, "split_ms": round(t_split, 4), "single_ms": round(t_single, 4), "dp": {}}
+            for t0 in range(4):
+                for t1 in (range(4) if two else (t0,)):
+                    terms = t0 | (t1 << 2)
+                    share = (k0 * bin(t0).count("1") + k1 * bin(t1).count("1")) / (2.0 * (k0 + k1))
+                    t_opt = t_single + (t_split - t_single) * share
+                    if terms == 15 or (not two and t0 == 3):
+                        err = 0.0
+                    else:
+                        ref.set_op_terms(i, terms)
+                        err = float(np.abs(ref.forward_tiles(probe_tiles) - want).max())
+                        ref.set_op_terms(i, 15)
+                    opts.append((terms if two else (t0 | t0 << 2), err, t_opt))
+                    rec["dp"][f"{t0}{t1}" if two else f"{t0}"] = err
+            options[i] = opts
+            layers.append(rec)
+            if verbose:
+                print(f"[calibrate] {name:14s} split {t_split:.3f} ms single {t_single:.3f} ms  dp by terms {rec['dp']}", flush=True)
+        eff, chosen, d_mixed, rounds = 0.9 * budget, None, None, 0
+        while True:
+            rounds += 1
+            chosen = choose_op_terms(options, eff)
+            for i, t in chosen.items():
+                ref.set_op_terms(i, t)
+            d_mixed = float(np.abs(ref.forward_tiles(probe_tiles) - want).max())
+            if d_mixed <= budget or rounds >= 8:
+                break
+            eff *= 0.85
+        if d_mixed > budget:
+            chosen = {i: 15 for i in chosen}
+            d_mixed = 0.0
+    names = {i: n for i, n, _ in srcs}
+    pred = float(np.sqrt(sum(next(e for tt, e, _ in options[i] if tt == t) ** 2 for i, t in chosen.items())))
+    est = sum(next(tm for tt, _, tm in options[i] if tt == t) for i, t in chosen.items())
+    all_split = all(t == 15 for t in chosen.values())
+    report.update({"layers": layers, "op_terms": {names[i]: [t & 3, t >> 2] for i, t in chosen.items()},
+                   "single_layers": [names[i] for i, t in chosen.items() if t == 0],
+                   "partial_layers": [names[i] for i, t in chosen.items() if t not in (0, 15)],
+                   "mixed_vs_split3_max_abs_dp": d_mixed, "predicted_quadrature_dp": pred, "rounds": rounds,
+                   "est_tensor_ms": {"chosen": est, "single": sum(prof_single[i]["ms"] for i in chosen),
+                                     "split3": sum(prof_split[i]["ms"] for i in chosen)},
+                   "chosen": "split3" if all_split else "mixed"})
+    return ("split3" if all_split else "mixed"), ({} if all_split else dict(chosen)), report
 
 
 class Engine:
@@ -354,12 +432,13 @@ class Engine:
     all-'single' if that fits, otherwise the error-budgeted per-layer 'mixed' selection, which may end at 'split3'."""
 
     def __init__(self, model: Model, device: int = 0, precision: str = "default", max_batch_tiles: int = 0,
-                 probe_tiles: Optional[np.ndarray] = None, single_mask: int = 0):
+                 probe_tiles: Optional[np.ndarray] = None, single_mask: int = 0, op_terms: Optional[Dict[int, int]] = None):
         self.auto_report = None
         self.single_mask = 0
+        self.op_terms = dict(op_terms) if op_terms else {}
         if precision == "auto":
-            chosen, mask, report = calibrate(model, device, probe_tiles)
-            final = Engine(model, device, chosen, max_batch_tiles, single_mask=mask)
+            chosen, terms, report = calibrate(model, device, probe_tiles)
+            final = Engine(model, device, chosen, max_batch_tiles, op_terms=terms)
             self.__dict__.update(final.__dict__)
             final._h = None
             self.auto_report = report
@@ -394,7 +473,12 @@ class Engine:
             for d in range(a.ndim):
                 arr[i].shape[d] = a.shape[d]
         h = C.c_void_p()
-        check(L.umx_create(C.byref(desc), arr, len(names), device, C.byref(h)))
+        if self.op_terms:               # per op and per source: which hi/lo correction terms (umx_create_ex)
+            n_ops = max(self.op_terms) + 1
+            ot = (C.c_int32 * n_ops)(*[int(self.op_terms.get(i, -1)) for i in range(n_ops)])
+            check(L.umx_create_ex(C.byref(desc), arr, len(names), device, ot, n_ops, C.byref(h)))
+        else:
+            check(L.umx_create(C.byref(desc), arr, len(names), device, C.byref(h)))
         self._h = h
         self._lock = threading.Lock()
 
@@ -581,6 +665,10 @@ class Engine:
             check(lib().umx_infer_images(self._h, arr, n, float(mean), float(std), _lib.UMX_F_CLI_QUANT if cli_quant else 0))
         return outs
 
+    def set_op_terms(self, op_index: int, terms: int) -> None:
+        """Calibration aid (split3 engines only): correction terms of one op, t0 | t1 << 2."""
+        check(lib().umx_set_op_terms(self._h, int(op_index), int(terms)))
+
     # -- instrumentation -----------------------------------------------------------------------
     def set_stream(self, cuda_stream: int) -> None:
         check(lib().umx_set_stream(self._h, int(cuda_stream)))
@@ -622,15 +710,15 @@ class MultiEngine:
     run the same arithmetic."""
 
     def __init__(self, model: Model, devices: Sequence[int], precision: str = "default", max_batch_tiles: int = 0,
-                 probe_tiles: Optional[np.ndarray] = None, single_mask: int = 0):
+                 probe_tiles: Optional[np.ndarray] = None, single_mask: int = 0, op_terms: Optional[Dict[int, int]] = None):
         if not devices:
             raise ValueError("MultiEngine needs at least one device")
         self.auto_report = None
         if precision == "auto":
-            precision, single_mask, self.auto_report = calibrate(model, devices[0], probe_tiles)
-        self.engines = [Engine(model, d, precision, max_batch_tiles, single_mask=single_mask) for d in devices]
+            precision, op_terms, self.auto_report = calibrate(model, devices[0], probe_tiles)
+        self.engines = [Engine(model, d, precision, max_batch_tiles, single_mask=single_mask, op_terms=op_terms) for d in devices]
         self.model = model
-        self.precision, self.single_mask = self.engines[0].precision, self.engines[0].single_mask
+        self.precision, self.single_mask, self.op_terms = self.engines[0].precision, self.engines[0].single_mask, self.engines[0].op_terms
         self.S, self.C, self.K = self.engines[0].S, self.engines[0].C, self.engines[0].K
 
     def close(self) -> None:
