@@ -243,7 +243,7 @@ def choose_model(name: str, probe_of):
     return modelzoo.synthetic_model(name, seed=0, logit_gain=gain), gain
 
 
-def stitched_crop_check(model, img, premap, scale: float, got_u8_crop_fn, max_tiles: int = 150):
+def stitched_crop_check(model, img, premap, scale: float, got_u8_crop_fn, max_tiles: int = 150, rows_available: int = 0):
     """A crop of the TIMED uint8 output vs the oracle pipeline (prepare -> PI2D tile loop -> fp32 UNet -> stitch ->
     uint8 [-> resize back -> uint8]) on the same crop.  Tiles that lie fully inside the crop are identical to the
     whole-slide tiles, so output pixels covered only by such tiles must agree within 1 level."""
@@ -273,6 +273,8 @@ def stitched_crop_check(model, img, premap, scale: float, got_u8_crop_fn, max_ti
     else:
         v = rc if full else (n_c - 1) * sub - m
     v = max(1, min(v, rc))
+    if rows_available:                                       # several GPUs: rank 0 only holds the rows of its own band
+        v = max(1, min(v, rows_available))
     got = got_u8_crop_fn(v)
     d = np.abs(got.astype(np.int16) - want[:, :v, :v].astype(np.int16))
     return {"region": f"top-left {v}x{v} px of the timed output", "max_abs_u8_diff": int(d.max()),
@@ -442,7 +444,8 @@ def run_workload(name: str, args, steps: int, warmup: int, main: bool, reuse=Non
     # ---- stitched uint8: crop of the timed (resident) output vs the oracle pipeline
     crop_check = None
     if rank == 0 and args.crop_check:
-        crop_check = stitched_crop_check(model, img, premap, scale, lambda v: d_out[:, :v, :v].cpu().numpy())
+        crop_check = stitched_crop_check(model, img, premap, scale, lambda v: d_out[:, :v, :v].cpu().numpy(),
+                                         rows_available=r1 if world > 1 else 0)
 
     # ---- multi-GPU: every band of the e2e output, bit for bit, against ONE GPU doing the whole slide
     bands_ok = None

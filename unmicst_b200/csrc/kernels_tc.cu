@@ -178,7 +178,7 @@ struct TileDecoder {
     uint32_t nt_mul; int n_ntiles, ph_shift, per_unit, rank, bn, bx_shift, bxy_shift, bw, bh;
     __device__ __forceinline__ void init(const TcConvParams& p, int per_unit_, int rank_) {
         n_ntiles = p.n_ntiles; nt_mul = (uint32_t)((0x100000000ull + n_ntiles - 1) / (uint32_t)n_ntiles);
-        ph_shift = p.nphase == 4 ? 2 : 0; per_unit = per_unit_; rank = rank_; bn = p.bn; bw = p.bw; bh = p.bh;
+        ph_shift = p.nphase == 4 ? (p.merge_px ? 1 : 2) : 0; per_unit = per_unit_; rank = rank_; bn = p.bn; bw = p.bw; bh = p.bh;
         bx_shift = 31 - __clz(p.in_w / p.bw); bxy_shift = bx_shift + 31 - __clz(p.in_h / p.bh);
     }
     __device__ __forceinline__ TileCoord operator()(int item) const {
@@ -510,7 +510,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int m_tiles = (p.bn > 1) ? (p.n_tiles + p.bn - 1) / p.bn : p.n_tiles * (p.in_w / p.bw) * (p.in_h / p.bh);
     const int per_unit = PAIR ? 2 : 1;
     const int m_units = (m_tiles + per_unit - 1) / per_unit;
-    const int total = p.nphase * m_units * p.n_ntiles;
+    // conv-transpose with merge_px: a work item covers the two sub-pixel phases (px = 0, 1) of one output row parity;
+    // they share every input patch and fill two n_t-column halves of one accumulator stage
+    const int nsub = p.merge_px ? 2 : 1;
+    const int total = (p.nphase / nsub) * m_units * p.n_ntiles;
     const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int item_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int nch0 = (p.c0 + 63) >> 6, nch1 = (p.c1 + 63) >> 6;
@@ -558,7 +561,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 int b_tile = item0, b_cb = 0;
                 TileCoord tb = decode(b_tile);
                 auto issue_b = [&]() {
-                    const TcPhaseGrid g = p.grid[tb.phase];
+                  for (int sub = 0; sub < nsub; ++sub) {
+                    const TcPhaseGrid g = p.grid[tb.phase * nsub + sub];
                     const int ncol = tb.n_idx * n_t + (PAIR ? rank * (n_t / 2) : 0);
                     const bool second = b_cb >= nch0;
                     const int cc = (second ? b_cb - nch0 : b_cb) * 64;
@@ -580,6 +584,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         }
                         if (++sb == nb_stages) { sb = 0; pb ^= 1; }
                     }
+                  }
                     if (++b_cb == n_chunks) { b_cb = 0; b_tile += item_step; if (b_tile < total) tb = decode(b_tile); }
                 };
                 // order per slab s: weights(s+1), then patch(s+n_stages-1): the wait for a free patch slot (= the MMAs of
@@ -683,16 +688,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const bool resident = p.b_resident != 0;
                 if (resident && item0 < total) { mbar_wait(fullB0, 0); tc_fence_after(); }
                 for (int tile = item0; tile < total; tile += item_step) {
-                    const TcPhaseGrid g = p.grid[decode(tile).phase];
-                    // A offset (in 16-byte units) of tap (iy, ix) inside the patch: off0 + iy*sy + ix*sx
-                    const int sx = g.dstep * 8, sy = g.dstep * prow * 8, row_back = sy - g.nx * sx;
-                    const uint32_t off0 = (uint32_t)(((g.dy0 + hy0) * prow + g.dx0 + hx0) * 8);
+                    const int ph0 = decode(tile).phase * nsub;
                     clk.lap(c_work);
                     mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
                     clk.lap(c_wt);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccStride);
-                    uint32_t accumulate = 0;
+                    uint32_t accumulate0 = 0, accumulate1 = 0;      // per sub-phase accumulator (merge_px)
                     for (int cb = 0; cb < n_chunks; ++cb) {
                         const bool second = cb >= nch0;
                         const int nk = one_mma ? 1 : (cb == nch0 - 1 ? nk_last0 : (cb == n_chunks - 1 ? nk_last1 : 4));
@@ -702,28 +704,36 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         tc_fence_after();
                         const uint32_t a_lo0 = desc_lo(smem_u32(smem) + (uint32_t)(sa * stage_bytes));
                         const bool centre_only = second && a1c;
-                        const int te = centre_only ? 1 : g.ntaps;
-                        uint32_t a_lo = a_lo0 + (centre_only ? (uint32_t)((hy0 * prow + hx0) * 8) : off0);
-                        int ix = 0;
-                        if (resident) {
-                            // weights stay put: slab cb's taps start at cb * gb tiles, addressed by their device tap index
-                            // (a centre-only slab keeps just that one tap, so the slabs after it start gb - 1 tiles earlier)
-                            const uint32_t r_off = (uint32_t)((second && a1c ? nch0 * gb + (cb - nch0) : cb * gb) * b_bytes);
-                            const uint32_t b_lo = desc_lo(smem_u32(smem_b) + r_off) + (centre_only ? 0u : (uint32_t)g.wi0 * b16);
-                            if (exp_mma & 128) {}
-                            else halo_taps_terms<PAIR>(split ? (second ? terms1 : terms0) : 0, nk, te, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, g.nx, ix, accumulate);
-                        } else
-                        for (int t0 = 0; t0 < te; t0 += gb) {
-                            const int ng = min(gb, te - t0);
-                            clk.lap(c_work);
-                            mbar_wait(fullB0 + 8 * sb, pb);
-                            clk.lap(c_wb);
-                            tc_fence_after();
-                            const uint32_t b_lo = desc_lo(smem_u32(smem_b) + (uint32_t)(sb * gb * b_bytes));
-                            if (exp_mma & 128) {}                 // timing experiment: the issue loop without the MMAs
-                            else halo_taps_terms<PAIR>(split ? (second ? terms1 : terms0) : 0, nk, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, g.nx, ix, accumulate);
-                            if (PAIR) umma_commit_pair(emptyB0 + 8 * sb); else umma_commit(emptyB0 + 8 * sb);
-                            if (++sb == nb_stages) { sb = 0; pb ^= 1; }
+                        for (int sub = 0; sub < nsub; ++sub) {
+                            const TcPhaseGrid g = p.grid[ph0 + sub];
+                            // A offset (in 16-byte units) of tap (iy, ix) inside the patch: off0 + iy*sy + ix*sx
+                            const int sx = g.dstep * 8, sy = g.dstep * prow * 8, row_back = sy - g.nx * sx;
+                            const uint32_t off0 = (uint32_t)(((g.dy0 + hy0) * prow + g.dx0 + hx0) * 8);
+                            const uint32_t tmem_ds = tmem_d + (uint32_t)(sub * p.n_t);
+                            uint32_t& accumulate = sub ? accumulate1 : accumulate0;
+                            const int te = centre_only ? 1 : g.ntaps;
+                            uint32_t a_lo = a_lo0 + (centre_only ? (uint32_t)((hy0 * prow + hx0) * 8) : off0);
+                            int ix = 0;
+                            if (resident) {
+                                // weights stay put: slab cb's taps start at cb * gb tiles, addressed by their device tap index
+                                // (a centre-only slab keeps just that one tap, so the slabs after it start gb - 1 tiles earlier)
+                                const uint32_t r_off = (uint32_t)((second && a1c ? nch0 * gb + (cb - nch0) : cb * gb) * b_bytes);
+                                const uint32_t b_lo = desc_lo(smem_u32(smem_b) + r_off) + (centre_only ? 0u : (uint32_t)g.wi0 * b16);
+                                if (exp_mma & 128) {}
+                                else halo_taps_terms<PAIR>(split ? (second ? terms1 : terms0) : 0, nk, te, tmem_ds, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, g.nx, ix, accumulate);
+                            } else
+                            for (int t0 = 0; t0 < te; t0 += gb) {
+                                const int ng = min(gb, te - t0);
+                                clk.lap(c_work);
+                                mbar_wait(fullB0 + 8 * sb, pb);
+                                clk.lap(c_wb);
+                                tc_fence_after();
+                                const uint32_t b_lo = desc_lo(smem_u32(smem_b) + (uint32_t)(sb * gb * b_bytes));
+                                if (exp_mma & 128) {}                 // timing experiment: the issue loop without the MMAs
+                                else halo_taps_terms<PAIR>(split ? (second ? terms1 : terms0) : 0, nk, ng, tmem_ds, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, g.nx, ix, accumulate);
+                                if (PAIR) umma_commit_pair(emptyB0 + 8 * sb); else umma_commit(emptyB0 + 8 * sb);
+                                if (++sb == nb_stages) { sb = 0; pb ^= 1; }
+                            }
                         }
                         if (PAIR) umma_commit_pair(empty0 + 8 * sa); else umma_commit(empty0 + 8 * sa);
                         if (++sa == n_stages) { sa = 0; pa ^= 1; }
@@ -805,7 +815,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const bool valid = n < n_tiles && !nostore;
             int oy, ox; bool writer = valid;
             if (e.pool) { oy = y >> 1; ox = x >> 1; writer = valid && !(y & 1) && !(x & 1); }
-            else if (os == 2) { oy = 2 * y + (t.phase >> 1); ox = 2 * x + (t.phase & 1); }
+            else if (os == 2) { oy = 2 * y + (nsub == 2 ? t.phase : (t.phase >> 1)); ox = 2 * x + (nsub == 2 ? 0 : (t.phase & 1)); }
             else { oy = y; ox = x; }
             const int64_t opix = ((int64_t)n * oh_ + oy) * ow_ + ox;
             const int co0 = t.n_idx * n_t + g_lo * 8;              // first output channel of this warp's columns
@@ -818,7 +828,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             mbar_wait_relaxed(tfull0 + 8 * acc, acc_phase);
             clk.lap(c_wt);
             tc_fence_after();
-            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride) + (uint32_t)(g_lo * 8);
+          for (int sp = 0; sp < nsub; ++sp) {        // merge_px: the second half of the stage holds the px = 1 phase -> the pixel one to the right
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride) + (uint32_t)(sp * n_t + g_lo * 8);
+            if (sp) { of += e.cout; oh += e.out_cs; }
             // the TMEM load of the next chunk is in flight while the current one is processed; an odd first group is
             // taken alone so that every 16-column chunk starts on a 32-byte boundary of the fp16 row (256-bit stores)
             uint32_t ra[16], rb[16], rt[8];
@@ -850,6 +862,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 epi_chunk<8, SKIPC, TOPK>(p, e, rt, cb16 + n_full * 16, xs, writer, of16 + n_full * 16, oh16 + n_full * 16, z);
                 __syncwarp();
             }
+          }
             if (TOPK > 0) {
                 // the warps of a lane quarter hold the column shares of each pixel: combine the partial logits
                 float4* zs = reinterpret_cast<float4*>(s_z) + (acc * (kEpiSub - 1) * 128 + m);
@@ -969,7 +982,7 @@ cudaError_t launch_tc_conv(const CUtensorMap& a0, const CUtensorMap& a1, const C
                            const TcConvParams& p, int num_sms, cudaStream_t s) {
     const int m_tiles = (p.bn > 1) ? (p.n_tiles + p.bn - 1) / p.bn : p.n_tiles * (p.in_w / p.bw) * (p.in_h / p.bh);
     const int per_unit = p.pair ? 2 : 1;
-    const int total = p.nphase * ((m_tiles + per_unit - 1) / per_unit) * p.n_ntiles;
+    const int total = (p.nphase / (p.merge_px ? 2 : 1)) * ((m_tiles + per_unit - 1) / per_unit) * p.n_ntiles;
     if (total == 0) return cudaSuccess;
     int grid = total * per_unit < num_sms ? total * per_unit : num_sms;
     if (p.pair) grid &= ~1;

@@ -610,6 +610,10 @@ int lower_conv_tc(umx_handle* h, Op& op) {
             // patch is consumed (a weight ring shorter than a slab's taps): a deadlock, so such layers run in plain mode
             if (tp.b_stages < 2 || (tp.stages < 3 && !tp.b_resident)) { tp.halo = 0; tp.halo_nh = 0; tp.bw = std::min(a0.w, 16); tp.bh = std::min(a0.h, 128 / tp.bw); tp.bn = 128 / (tp.bw * tp.bh); }
         }
+        {
+            const char* e = getenv("UMX_TC_MERGE_PX");
+            tp.merge_px = (tp.halo && sp.transpose && tp.nphase == 4 && 2 * tp.n_t <= 256 && (e ? atoi(e) : 1)) ? 1 : 0;
+        }
         tp.kslab = 1;
         if (!tp.halo) {
             // single precision issues one MMA per K step: put two slabs behind each barrier round trip

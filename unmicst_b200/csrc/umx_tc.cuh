@@ -23,6 +23,8 @@ struct TcConvParams {
     int32_t n_t;                 // GEMM N per CTA tile (multiple of 16, <= 256)
     int32_t n_ntiles;            // ceil(cout / n_t)
     int32_t nphase, os;          // conv: 1,1   conv-transpose: 4,2
+    int32_t merge_px;            // conv-transpose in halo mode: a work item covers both px phases of a row parity (shared patches, two n_t-column
+                                 // accumulator halves): half the patch loads, barrier round trips and epilogue hand-overs
     TcPhaseGrid grid[4];         // per phase tap grid (conv 3x3/5x5: 1 phase; conv-transpose: 4 phases, <= 9 taps)
     int32_t planes;              // 1: fp16 operands, 1 MMA/product; 2: hi/lo split, up to 3 MMAs/product
     int32_t planes_a, planes_b;  // planes a slot holds (layout): A hi [+ lo], B hi [+ lo]; fixed when the op is lowered
