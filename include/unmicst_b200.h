@@ -216,6 +216,11 @@ int64_t umx_debug_buffer(umx_handle* h, const char* name, int32_t n_tiles, float
 /* Kernels launched by this handle since creation (umx_*: claim for "gpu_launches"). */
 int64_t umx_launch_count(umx_handle* h);
 
+/* How op `op_index` was lowered (diagnostics, calibration): out[0..11] = on the tensor path, halo mode, CTA pairs, patch /
+ * ring slots, weight slots, taps per weight slot, weights resident in shared memory, conv-transpose px merge, planes per
+ * activation slot, planes per weight slot, correction terms of source 0, of source 1. */
+int umx_op_info(umx_handle* h, int32_t op_index, int32_t* out, int32_t capacity);
+
 /* Pinned host memory for callers that want full-rate async copies. */
 void* umx_host_alloc(int64_t bytes);
 void  umx_host_free(void* p);

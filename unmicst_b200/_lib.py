@@ -78,6 +78,7 @@ SYMBOLS = {
     "umx_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "umx_profile_read": (C.c_int, [C.c_void_p, C.POINTER(umx_prof_entry), C.c_int32, C.c_int32]),
     "umx_launch_count": (C.c_int64, [C.c_void_p]),
+    "umx_op_info": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32]),
     "umx_debug_buffer": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_int32, C.c_void_p, C.c_int64]),
     "umx_host_alloc": (C.c_void_p, [C.c_int64]),
     "umx_host_free": (None, [C.c_void_p]),

@@ -603,11 +603,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                                 if (second && a1c) {        // 1x1 term: only its centre tap exists (one-tap box)
                                     if (PAIR) tma_load_4d_pair(db, &mapB1, fullB0, kc, ncol, ctap, 0);
                                     else tma_load_4d(db, &mapB1, fullB0, kc, ncol, ctap, 0);
-                                    db += b_bytes;
+                                    db += p.res_c_planes * b_plane_bytes;          // hi [+ lo when that source uses the a_hi*w_lo term]
                                 } else {
                                     if (PAIR) tma_load_4d_pair(db, &mapB, fullB0, kc, ncol, 0, 0);
                                     else tma_load_4d(db, &mapB, fullB0, kc, ncol, 0, 0);
-                                    db += gb * b_bytes;
+                                    db += gb * b_plane_bytes;                      // resident main slabs hold the hi plane only
                                 }
                             }
                         }
@@ -717,10 +717,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             if (resident) {
                                 // weights stay put: slab cb's taps start at cb * gb tiles, addressed by their device tap index
                                 // (a centre-only slab keeps just that one tap, so the slabs after it start gb - 1 tiles earlier)
-                                const uint32_t r_off = (uint32_t)((second && a1c ? nch0 * gb + (cb - nch0) : cb * gb) * b_bytes);
+                                const uint32_t r_off = (uint32_t)((second && a1c ? nch0 * gb + (cb - nch0) * p.res_c_planes : cb * gb) * b_plane_bytes);
                                 const uint32_t b_lo = desc_lo(smem_u32(smem_b) + r_off) + (centre_only ? 0u : (uint32_t)g.wi0 * b16);
                                 if (exp_mma & 128) {}
-                                else halo_taps_terms<PAIR>(split ? (second ? terms1 : terms0) : 0, nk, te, tmem_ds, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, g.nx, ix, accumulate);
+                                else halo_taps_terms<PAIR>(split ? (second ? terms1 : terms0) : 0, nk, te, tmem_ds, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, centre_only ? b16 : bp16, b16, sx, row_back, g.nx, ix, accumulate);
                             } else
                             for (int t0 = 0; t0 < te; t0 += gb) {
                                 const int ng = min(gb, te - t0);

@@ -532,7 +532,6 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     tp.planes = planes;
     tp.terms0 = op_terms(h, op) & 3; tp.terms1 = (op_terms(h, op) >> 2) & 3;
     if (!a1) tp.terms1 = tp.terms0;             // single source: one setting
-    tp.planes_a = ((tp.terms0 | tp.terms1) & 2) ? 2 : 1; tp.planes_b = ((tp.terms0 | tp.terms1) & 1) ? 2 : 1;
     if (const char* e = getenv("UMX_TC_TERMS")) {          // experiment: "name:t0:t1;name:t0:t1" picks the correction terms per source
         std::string spec(e);
         size_t pos = 0;
@@ -547,6 +546,7 @@ int lower_conv_tc(umx_handle* h, Op& op) {
             pos = end + 1;
         }
     }
+    tp.planes_a = ((tp.terms0 | tp.terms1) & 2) ? 2 : 1; tp.planes_b = ((tp.terms0 | tp.terms1) & 1) ? 2 : 1;
     {
         const char* e = getenv("UMX_TC_PAIR");
         tp.pair = (e ? atoi(e) : 1) && ((tp.n_t / 2) % 8 == 0) ? 1 : 0;
@@ -598,9 +598,15 @@ int lower_conv_tc(umx_handle* h, Op& op) {
             {
                 const int nc0 = (tp.c0 + 63) / 64, nc1 = (tp.c1 + 63) / 64, n_chunks = nc0 + nc1;
                 // (the slabs of a 1x1 term exist at the centre tap only: one tile each instead of ntaps_w)
-                const size_t res = ((size_t)nc0 * ntaps_w + (size_t)nc1 * (tp.a1_center ? 1 : ntaps_w)) * bb;
+                // resident tiles hold the hi plane; the one-tile slabs of a 1x1 term may add their lo plane
+                const size_t tile = (size_t)(tp.pair ? tp.n_t / 2 : tp.n_t) * 128;
+                const bool main_hi_only = (tp.terms0 & 1) == 0 && (tp.a1_center || (tp.terms1 & 1) == 0);
+                tp.res_c_planes = (tp.a1_center && (tp.terms1 & 1)) ? 2 : 1;
+                const size_t res = ((size_t)nc0 * ntaps_w + (size_t)nc1 * (tp.a1_center ? tp.res_c_planes : ntaps_w)) * tile;
                 const char* e = getenv("UMX_TC_RESIDENT");
-                if ((e ? atoi(e) : 1) && tp.n_ntiles == 1 && ntaps_w <= 9 && planes == 1 && (tp.terms0 | tp.terms1) == 0 && budget >= res + 3 * ab) {
+                // (weights hi plane only for every full slab: no a_hi*w_lo term there; with both activation planes in a patch
+                // slot two slots are accepted - in this mode nothing but patches moves, so no patch waits behind a weight load)
+                if ((e ? atoi(e) : 1) && tp.n_ntiles == 1 && ntaps_w <= 9 && main_hi_only && budget >= res + (tp.planes_a == 2 ? 2 : 3) * ab) {
                     tp.b_resident = 1; tp.gb = ntaps_w; tp.b_stages = n_chunks; tp.b_res_bytes = (int32_t)res;
                     tp.stages = (int)std::min<size_t>(6, (budget - res) / ab);
                 }
@@ -695,11 +701,11 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     UMX_CUDA_TRY(cudaMalloc(&dw, wh.size() * sizeof(__half)));
     h->dev_allocs.push_back(reinterpret_cast<float*>(dw));
     UMX_CUDA_TRY(cudaMemcpy(dw, wh.data(), wh.size() * sizeof(__half), cudaMemcpyHostToDevice));
-    int rc = make_weight_tensor_map(&op.mapB, dw, planes_b, taps_dev, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, planes_b, box_taps);
+    int rc = make_weight_tensor_map(&op.mapB, dw, planes_b, taps_dev, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, tp.b_resident ? 1 : planes_b, box_taps);
     if (rc) { set_error("%s: cuTensorMapEncodeTiled(weights) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
     op.mapB1 = op.mapB;
     if (tp.b_resident && tp.a1_center) {
-        rc = make_weight_tensor_map(&op.mapB1, dw, planes_b, taps_dev, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, planes_b, 1);
+        rc = make_weight_tensor_map(&op.mapB1, dw, planes_b, taps_dev, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, tp.res_c_planes, 1);
         if (rc) { set_error("%s: cuTensorMapEncodeTiled(weights, one tap) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
     }
     if (!a0.dh || (a1 && !a1->dh)) { set_error("%s: fp16 source buffer missing", op.name.c_str()); return UMX_EINVAL; }
@@ -1123,6 +1129,18 @@ int umx_profile_read(umx_handle* h, umx_prof_entry* out, int32_t capacity, int32
 }
 
 int64_t umx_launch_count(umx_handle* h) { return h ? h->launches : 0; }
+
+int umx_op_info(umx_handle* h, int32_t op_index, int32_t* out, int32_t capacity) {
+    if (!h || !out || capacity < 12 || op_index < 0 || op_index >= (int)h->ops.size()) { set_error("umx_op_info: bad argument"); return UMX_EINVAL; }
+    const Op& op = h->ops[op_index];
+    const TcConvParams& tp = op.tcp;
+    const bool tc = op.kind == OP_CONV && op.use_tc;
+    const int v[12] = {tc ? 1 : 0, tc ? tp.halo : 0, tc ? tp.pair : 0, tc ? tp.stages : 0, tc ? tp.b_stages : 0, tc ? tp.gb : 0,
+                       tc ? tp.b_resident : 0, tc ? tp.merge_px : 0, tc ? tp.planes_a : 0, tc ? tp.planes_b : 0,
+                       tc ? tp.terms0 : 0, tc ? tp.terms1 : 0};
+    for (int i = 0; i < 12; ++i) out[i] = v[i];
+    return UMX_OK;
+}
 
 int64_t umx_debug_buffer(umx_handle* h, const char* name, int32_t n_tiles, float* out, int64_t capacity) {
     if (!h || !name || !out || n_tiles < 0) { set_error("umx_debug_buffer: bad argument"); return UMX_EINVAL; }

@@ -358,10 +358,11 @@ def calibrate(model: Model, device: int = 0, probe_tiles: Optional[np.ndarray] =
         e.profile_enable(False)
         return prof
 
+    srcs = [(i, n, ks) for i, n, ks in tensor_op_sources(model)]
     with Engine(model, device, "single", batch) as es:
         got_single = es.forward_tiles(probe_tiles)
         prof_single = profile_of(es)
-    srcs = [(i, n, ks) for i, n, ks in tensor_op_sources(model)]
+        resident = {i for i, _, _ in srcs if es.op_info(i)["resident"]}       # weight-stationary layers (64 x 64 grids)
     with Engine(model, device, "split3", batch) as ref:
         want = ref.forward_tiles(probe_tiles)
         d_single = float(np.abs(got_single - want).max())
@@ -371,44 +372,75 @@ def calibrate(model: Model, device: int = 0, probe_tiles: Optional[np.ndarray] =
             report["chosen"] = "single"
             return "single", {}, report
         prof_split = profile_of(ref)
-        options: Dict[int, List[Tuple[int, float, float]]] = {}
+        # per op: (terms, error alone, time by the linear model, time if hi-only weights stay resident)
+        measured: Dict[int, List[Tuple[int, float, float, float]]] = {}
         layers = []
         for i, name, ks in srcs:
             two = len(ks) > 1
             k0, k1 = ks[0], (ks[1] if two else 0.0)
             t_single, t_split = prof_single[i]["ms"], max(prof_split[i]["ms"], prof_single[i]["ms"])
-            opts: List[Tuple[int, float, float]] = []
+            opts: List[Tuple[int, float, float, float]] = []
             rec = {"op": i, "name": name, "split_ms": round(t_split, 4), "single_ms": round(t_single, 4), "dp": {}}
             for t0 in range(4):
                 for t1 in (range(4) if two else (t0,)):
                     terms = t0 | (t1 << 2)
                     share = (k0 * bin(t0).count("1") + k1 * bin(t1).count("1")) / (2.0 * (k0 + k1))
-                    t_opt = t_single + (t_split - t_single) * share
+                    t_lin = t_single + (t_split - t_single) * share
+                    # a layer whose weights stay in shared memory in single mode keeps them there as long as no
+                    # a_hi*w_lo term asks for the lo plane of the weights: its time then scales with the MMAs issued
+                    # (measured on B200: 1.76x for twice the MMAs; a partial split that streams both weight planes costs
+                    # ~20 % more than the MMA share suggests)
+                    # (the one-tile slab of a 1x1 term - a tap-expanded raw input, K < 64 - may keep its lo plane too)
+                    hi_only = not (t0 & 1) and (not two or not (t1 & 1) or k1 < 64)
+                    t_res = t_single * (1.0 + 1.55 * share) if (i in resident and hi_only) else t_single + (t_split - t_single) * min(1.0, 1.2 * share)
                     if terms == 15 or (not two and t0 == 3):
                         err = 0.0
                     else:
                         ref.set_op_terms(i, terms)
                         err = float(np.abs(ref.forward_tiles(probe_tiles) - want).max())
                         ref.set_op_terms(i, 15)
-                    opts.append((terms if two else (t0 | t0 << 2), err, t_opt))
+                    opts.append((terms if two else (t0 | t0 << 2), err, t_lin, t_res if terms not in (0, 15) and not (not two and t0 in (0, 3)) else t_lin))
                     rec["dp"][f"{t0}{t1}" if two else f"{t0}"] = err
-            options[i] = opts
+            measured[i] = opts
             layers.append(rec)
             if verbose:
                 print(f"[calibrate] {name:14s} split {t_split:.3f} ms single {t_single:.3f} ms  dp by terms {rec['dp']}", flush=True)
-        eff, chosen, d_mixed, rounds = 0.9 * budget, None, None, 0
-        while True:
-            rounds += 1
-            chosen = choose_op_terms(options, eff)
-            for i, t in chosen.items():
-                ref.set_op_terms(i, t)
-            d_mixed = float(np.abs(ref.forward_tiles(probe_tiles) - want).max())
-            if d_mixed <= budget or rounds >= 8:
-                break
-            eff *= 0.85
-        if d_mixed > budget:
-            chosen = {i: 15 for i in chosen}
-            d_mixed = 0.0
+
+        def assign(col: int) -> Tuple[Dict[int, int], float, int]:
+            options = {i: [(x[0], x[1], x[2 + col]) for x in opts] for i, opts in measured.items()}
+            eff, rounds = 0.9 * budget, 0
+            while True:
+                rounds += 1
+                pick = choose_op_terms(options, eff)
+                for i, t in pick.items():
+                    ref.set_op_terms(i, t)
+                d = float(np.abs(ref.forward_tiles(probe_tiles) - want).max())
+                if d <= budget or rounds >= 8:
+                    break
+                eff *= 0.85
+            for i in pick:
+                ref.set_op_terms(i, 15)
+            if d > budget:
+                return {i: 15 for i in pick}, 0.0, rounds
+            return pick, d, rounds
+
+        cands = [assign(0)]
+        if resident:
+            alt = assign(1)
+            if alt[0] != cands[0][0]:
+                cands.append(alt)
+    # candidates are built for real and timed (the models above rank options, the clock decides between assignments)
+    timed = []
+    for pick, d, rounds in cands:
+        if all(t == 15 for t in pick.values()) or len(cands) == 1:
+            timed.append((None, pick, d, rounds))
+            continue
+        with Engine(model, device, "mixed", batch, op_terms=pick) as e:
+            prof = profile_of(e)
+        timed.append((sum(prof[i]["ms"] for i in pick), pick, d, rounds))
+    best = min(timed, key=lambda c: (c[0] is None, c[0] or 0.0)) if any(c[0] is not None for c in timed) else timed[0]
+    _, chosen, d_mixed, rounds = best
+    options = {i: [(x[0], x[1], x[2]) for x in opts] for i, opts in measured.items()}
     names = {i: n for i, n, _ in srcs}
     pred = float(np.sqrt(sum(next(e for tt, e, _ in options[i] if tt == t) ** 2 for i, t in chosen.items())))
     est = sum(next(tm for tt, _, tm in options[i] if tt == t) for i, t in chosen.items())
@@ -417,6 +449,8 @@ def calibrate(model: Model, device: int = 0, probe_tiles: Optional[np.ndarray] =
                    "single_layers": [names[i] for i, t in chosen.items() if t == 0],
                    "partial_layers": [names[i] for i, t in chosen.items() if t not in (0, 15)],
                    "mixed_vs_split3_max_abs_dp": d_mixed, "predicted_quadrature_dp": pred, "rounds": rounds,
+                   "weight_stationary_layers": [names[i] for i in sorted(resident)],
+                   "candidates_timed_ms": [None if c[0] is None else round(c[0], 4) for c in timed],
                    "est_tensor_ms": {"chosen": est, "single": sum(prof_single[i]["ms"] for i in chosen),
                                      "split3": sum(prof_split[i]["ms"] for i in chosen)},
                    "chosen": "split3" if all_split else "mixed"})
@@ -664,6 +698,14 @@ class Engine:
         with self._lock:
             check(lib().umx_infer_images(self._h, arr, n, float(mean), float(std), _lib.UMX_F_CLI_QUANT if cli_quant else 0))
         return outs
+
+    OP_INFO_FIELDS = ("tensor", "halo", "pair", "stages", "b_stages", "gb", "resident", "merge_px", "planes_a", "planes_b", "terms0", "terms1")
+
+    def op_info(self, op_index: int) -> Dict[str, int]:
+        """How op ``op_index`` was lowered (umx_op_info)."""
+        buf = (C.c_int32 * 12)()
+        check(lib().umx_op_info(self._h, int(op_index), buf, 12))
+        return dict(zip(self.OP_INFO_FIELDS, [int(v) for v in buf]))
 
     def set_op_terms(self, op_index: int, terms: int) -> None:
         """Calibration aid (split3 engines only): correction terms of one op, t0 | t1 << 2."""
