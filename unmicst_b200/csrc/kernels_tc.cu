@@ -480,7 +480,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tma_prefetch_desc(&mapA0);
         if (p.c1 > 0) tma_prefetch_desc(&mapA1);
         tma_prefetch_desc(&mapB);
-        if (p.b_resident && p.a1_center) tma_prefetch_desc(&mapB1);
+        if ((p.b_resident && p.a1_center) || p.b1_hi_only) tma_prefetch_desc(&mapB1);
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -570,6 +570,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     const int te = centre_only ? 1 : g.ntaps;
                     const int kc = (second ? c0s : 0) + cc;
                     const int wi0 = centre_only ? ctap : g.wi0;
+                    // a source without the a_hi*w_lo term fetches the hi plane of the weights only (mapB1: one-plane box)
+                    const bool hi_only = planes_b == 2 && p.b1_hi_only && !((second ? p.terms1 : p.terms0) & 1);
                     for (int t0 = 0; t0 < te; t0 += gb) {
                         clk.lap(c_work);
                         mbar_wait(emptyB0 + 8 * sb, pb ^ 1);
@@ -578,9 +580,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         const uint32_t db = smem_u32(smem_b) + (uint32_t)(sb * gb * b_bytes);
                         if (noload) { if (leader) mbar_arrive(fb); }
                         else {
-                            if (leader) mbar_expect_tx(fb, txB);
-                            if (PAIR) tma_load_4d_pair(db, &mapB, fb, kc, ncol, wi0 + t0, 0);
-                            else tma_load_4d(db, &mapB, fb, kc, ncol, wi0 + t0, 0);
+                            if (leader) mbar_expect_tx(fb, hi_only ? txB / 2 : txB);
+                            if (PAIR) tma_load_4d_pair(db, hi_only ? &mapB1 : &mapB, fb, kc, ncol, wi0 + t0, 0);
+                            else tma_load_4d(db, hi_only ? &mapB1 : &mapB, fb, kc, ncol, wi0 + t0, 0);
                         }
                         if (++sb == nb_stages) { sb = 0; pb ^= 1; }
                     }

@@ -704,6 +704,12 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     int rc = make_weight_tensor_map(&op.mapB, dw, planes_b, taps_dev, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, tp.b_resident ? 1 : planes_b, box_taps);
     if (rc) { set_error("%s: cuTensorMapEncodeTiled(weights) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
     op.mapB1 = op.mapB;
+    if (tp.halo && !tp.b_resident && planes_b == 2 && (!(tp.terms0 & 1) || (a1 && !(tp.terms1 & 1)))) {
+        // some source never multiplies the weights' lo plane: it streams one-plane boxes (the slot layout stays [hi taps][lo taps])
+        rc = make_weight_tensor_map(&op.mapB1, dw, planes_b, taps_dev, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, 1, box_taps);
+        if (rc) { set_error("%s: cuTensorMapEncodeTiled(weights, hi plane) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
+        tp.b1_hi_only = 1;
+    }
     if (tp.b_resident && tp.a1_center) {
         rc = make_weight_tensor_map(&op.mapB1, dw, planes_b, taps_dev, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, tp.res_c_planes, 1);
         if (rc) { set_error("%s: cuTensorMapEncodeTiled(weights, one tap) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
