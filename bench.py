@@ -419,8 +419,10 @@ def run_workload(name: str, args, steps: int, warmup: int, main: bool, reuse=Non
     for _ in range(warmup):
         resident()
     n_before = eng.launch_count
+    torch.cuda.nvtx.range_push("timed_resident")          # ncu --nvtx --nvtx-include "timed_resident/" profiles exactly these launches
     with ClockSampler(local, enabled=rank == 0) as clk:
         ms, own = timed(resident, steps)
+    torch.cuda.nvtx.range_pop()
     launches = eng.launch_count - n_before
     ms_per_step = ms / steps
     value = IH * IW / 1e6 / (ms_per_step / 1e3)

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libunmicst_b200.so")
+LIB_PATH = os.environ.get("UNMICST_B200_LIB") or os.path.join(HERE, "csrc", "libunmicst_b200.so")     # (override: A/B builds of tools/)
 
 UMX_ABI_VERSION = 1
 UMX_OK, UMX_EINVAL, UMX_ENOTENSOR, UMX_ECUDA, UMX_ENOMEM, UMX_ENODEVICE = 0, -1, -2, -3, -4, -5

@@ -64,32 +64,25 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
         : "=r"(ok) : "r"(bar), "r"(parity), "r"(ns) : "memory");
     return ok != 0;
 }
-// A pipeline bug must end in a trap, not in a hung GPU - but a wait that is merely slow (compute-sanitizer, a debugger,
-// time-sliced sharing, a clock collapse) must not poison the context: the limit is ELAPSED TIME (20 s on %globaltimer,
-// read once per 1024 failed polls, so the hot path - a wait that succeeds within a few polls - never touches it).
-constexpr unsigned long long kWaitLimitNs = 20ull * 1000ull * 1000ull * 1000ull;
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-__device__ __noinline__ void mbar_timed_out(uint32_t bar, uint32_t parity) {
-    // one line per stuck role is enough to read the pipeline state: warp 0 = TMA producer, warp 1 = MMA issuer, 2.. = epilogue
+// A pipeline bug must end in a trap, not in a hung GPU: a wait gives up after kSpinLimit failed polls.  A poll sleeps in
+// hardware until the phase completes or the hint elapses, so the limit is reached after 84 s (20 us hints) to 7 min
+// (100 us hints) of genuine waiting, and no sooner than ~0.2 s even if every poll returned at once (slow tools,
+// time slicing); no legitimate wait of these kernels lasts a millisecond.  The check is a counter on purpose:
+// anything heavier in this loop (a %globaltimer read, an out-of-line slow path: both tried) costs the single-thread
+// roles 5-15 % on the issue-bound layers and, as an ABI call, 5 MB of code.
+constexpr uint32_t kSpinLimit = 1u << 22;
+__device__ __forceinline__ void mbar_timed_out(uint32_t bar, uint32_t parity) {
+    // one line per stuck warp is enough to read the pipeline state: warp 0 = TMA producer, warp 1 = MMA issuer, 2.. = epilogue
     if ((threadIdx.x & 31) == 0 || threadIdx.x < 64)
-        printf("umx tc_conv: mbarrier wait exceeded 20 s (block %d warp %d thread %d, barrier at shared 0x%x, parity %u)\n",
+        printf("umx tc_conv: mbarrier wait timed out (block %d warp %d thread %d, barrier at shared 0x%x, parity %u)\n",
                blockIdx.x, threadIdx.x >> 5, threadIdx.x, bar, parity);
     __trap();
 }
 template <uint32_t HINT_NS>
 __device__ __forceinline__ void mbar_wait_impl(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
-    unsigned long long t0 = 0;
     while (!mbar_try_wait_hint(bar, parity, HINT_NS)) {
-        if ((++spins & 1023u) == 0) {
-            const unsigned long long now = globaltimer_ns();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > kWaitLimitNs) mbar_timed_out(bar, parity);
-        }
+        if (++spins > kSpinLimit) mbar_timed_out(bar, parity);
     }
 }
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) { mbar_wait_impl<20000u>(bar, parity); }
@@ -262,21 +255,29 @@ __device__ __forceinline__ void umma_slab(uint32_t tmem_d, uint32_t a_lo, uint32
 // Halo mode: the `ng` taps of one weight slot against one patch, as straight-line code for a compile-time number of
 // 16-channel steps (the gap between two MMAs of the single issuing thread must stay below the ~40-50 cycles one
 // N = 80 MMA takes, or the tensor pipe idles at every tap boundary).
-// TERMS (split layers): bit 0 = the a_hi * w_lo correction, bit 1 = the a_lo * w_hi correction; 0 = one MMA per product
+// Split layers add up to two correction MMAs per product (uniform in the single issuing thread): terms bit 0 = a_hi * w_lo,
+// bit 1 = a_lo * w_hi.  (One compile-time variant per term set made the kernel 16 straight-line copies large and cost the
+// issue-bound layers ~10 %: only "none" and "a_lo only" are compiled in, the rest branches on two uniform flags.)
+// TERMS: 0 = no correction, 2 = a_lo * w_hi only (the weight-stationary partial split of the 64 x 64 layers), -1 = chosen at run time.
 template <bool PAIR, int NK, int TERMS>
-__device__ __forceinline__ void halo_taps(int ng, uint32_t tmem_d, uint32_t& a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+__device__ __forceinline__ void halo_taps(int terms, int ng, uint32_t tmem_d, uint32_t& a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                           uint32_t idesc, uint32_t a_plane16, uint32_t bp16, uint32_t b16, int sx, int row_back,
                                           int nx, int& ix, uint32_t& accumulate) {
+    const bool w_lo = TERMS == -1 && (terms & 1), a_lo_t = TERMS == 2 || (TERMS == -1 && (terms & 2));
     for (int j = 0; j < ng; ++j, b_lo += b16) {
         umma_issue<PAIR>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
         accumulate = 1;
-        if (TERMS & 1) umma_acc<PAIR>(tmem_d, a_lo, a_hi, b_lo + bp16, b_hi, idesc);
-        if (TERMS & 2) umma_acc<PAIR>(tmem_d, a_lo + a_plane16, a_hi, b_lo, b_hi, idesc);
+        if (TERMS != 0) {
+            if (w_lo) umma_acc<PAIR>(tmem_d, a_lo, a_hi, b_lo + bp16, b_hi, idesc);
+            if (a_lo_t) umma_acc<PAIR>(tmem_d, a_lo + a_plane16, a_hi, b_lo, b_hi, idesc);
+        }
 #pragma unroll
         for (int k = 1; k < NK; ++k) {
             umma_acc<PAIR>(tmem_d, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc);
-            if (TERMS & 1) umma_acc<PAIR>(tmem_d, a_lo + 2 * k, a_hi, b_lo + bp16 + 2 * k, b_hi, idesc);
-            if (TERMS & 2) umma_acc<PAIR>(tmem_d, a_lo + a_plane16 + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc);
+            if (TERMS != 0) {
+                if (w_lo) umma_acc<PAIR>(tmem_d, a_lo + 2 * k, a_hi, b_lo + bp16 + 2 * k, b_hi, idesc);
+                if (a_lo_t) umma_acc<PAIR>(tmem_d, a_lo + a_plane16 + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc);
+            }
         }
         a_lo += sx;
         if (++ix == nx) { ix = 0; a_lo += row_back; }
@@ -284,24 +285,23 @@ __device__ __forceinline__ void halo_taps(int ng, uint32_t tmem_d, uint32_t& a_l
 }
 
 template <bool PAIR, int TERMS>
-__device__ __forceinline__ void halo_taps_nk(int nk, int ng, uint32_t tmem_d, uint32_t& a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+__device__ __forceinline__ void halo_taps_nk(int terms, int nk, int ng, uint32_t tmem_d, uint32_t& a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                              uint32_t idesc, uint32_t a_plane16, uint32_t bp16, uint32_t b16, int sx, int row_back,
                                              int nx, int& ix, uint32_t& accumulate) {
-    if (nk == 4) halo_taps<PAIR, 4, TERMS>(ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
-    else if (nk == 1) halo_taps<PAIR, 1, TERMS>(ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
-    else if (nk == 2) halo_taps<PAIR, 2, TERMS>(ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
-    else halo_taps<PAIR, 3, TERMS>(ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
+    if (nk == 4) halo_taps<PAIR, 4, TERMS>(terms, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
+    else if (nk == 1) halo_taps<PAIR, 1, TERMS>(terms, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
+    else if (nk == 2) halo_taps<PAIR, 2, TERMS>(terms, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
+    else halo_taps<PAIR, 3, TERMS>(terms, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
 }
 
-// per-slab dispatch on the correction terms of the slab's source (uniform in the single issuing thread)
+// per-slab dispatch on the correction terms of the slab's source
 template <bool PAIR>
 __device__ __forceinline__ void halo_taps_terms(int terms, int nk, int ng, uint32_t tmem_d, uint32_t& a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                                 uint32_t idesc, uint32_t a_plane16, uint32_t bp16, uint32_t b16, int sx, int row_back,
                                                 int nx, int& ix, uint32_t& accumulate) {
-    if (terms == 3) halo_taps_nk<PAIR, 3>(nk, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
-    else if (terms == 0) halo_taps_nk<PAIR, 0>(nk, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
-    else if (terms == 1) halo_taps_nk<PAIR, 1>(nk, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
-    else halo_taps_nk<PAIR, 2>(nk, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
+    if (terms == 0) halo_taps_nk<PAIR, 0>(0, nk, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
+    else if (terms == 2) halo_taps_nk<PAIR, 2>(2, nk, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
+    else halo_taps_nk<PAIR, -1>(terms, nk, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
 }
 
 // Everything the epilogue of one accumulator tile needs that does not change from item to item.
@@ -688,41 +688,49 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const uint32_t bp16 = (uint32_t)gb * b_plane16;
                 int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
                 const bool resident = p.b_resident != 0;
+                const uint32_t c_off = (uint32_t)((hy0 * prow + hx0) * 8);      // centre tap of the patch (1x1 term)
                 if (resident && item0 < total) { mbar_wait(fullB0, 0); tc_fence_after(); }
                 for (int tile = item0; tile < total; tile += item_step) {
                     const int ph0 = decode(tile).phase * nsub;
+                    // per sub-phase tap walk, once per item (the slab loop below must stay a handful of instructions per
+                    // slab: its single thread paces the N = 80 layers).  A offset (16-byte units) of tap (iy, ix) inside the
+                    // patch: off0 + iy*sy + ix*sx
+                    // (scalars, not arrays: anything indexed by the sub-phase would live in local memory)
+                    const TcPhaseGrid ga = p.grid[ph0], gb2 = p.grid[ph0 + nsub - 1];
+                    const int sx0 = ga.dstep * 8, rb0 = ga.dstep * prow * 8 - ga.nx * ga.dstep * 8, nx0 = ga.nx, nt0 = ga.ntaps;
+                    const uint32_t off0 = (uint32_t)(((ga.dy0 + hy0) * prow + ga.dx0 + hx0) * 8), wi0 = (uint32_t)ga.wi0 * b16;
+                    const int sx1 = gb2.dstep * 8, rb1 = gb2.dstep * prow * 8 - gb2.nx * gb2.dstep * 8, nx1 = gb2.nx, nt1 = gb2.ntaps;
+                    const uint32_t off1 = (uint32_t)(((gb2.dy0 + hy0) * prow + gb2.dx0 + hx0) * 8), wi1 = (uint32_t)gb2.wi0 * b16;
                     clk.lap(c_work);
                     mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
                     clk.lap(c_wt);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccStride);
-                    uint32_t accumulate0 = 0, accumulate1 = 0;      // per sub-phase accumulator (merge_px)
+                    uint32_t accum0 = 0, accum1 = 0;      // per sub-phase accumulator (merge_px)
                     for (int cb = 0; cb < n_chunks; ++cb) {
                         const bool second = cb >= nch0;
                         const int nk = one_mma ? 1 : (cb == nch0 - 1 ? nk_last0 : (cb == n_chunks - 1 ? nk_last1 : 4));
+                        const int tsel = split ? (second ? terms1 : terms0) : 0;
                         clk.lap(c_work);
                         mbar_wait(full0 + 8 * sa, pa);
                         clk.lap(c_wa);
                         tc_fence_after();
                         const uint32_t a_lo0 = desc_lo(smem_u32(smem) + (uint32_t)(sa * stage_bytes));
                         const bool centre_only = second && a1c;
-                        for (int sub = 0; sub < nsub; ++sub) {
-                            const TcPhaseGrid g = p.grid[ph0 + sub];
-                            // A offset (in 16-byte units) of tap (iy, ix) inside the patch: off0 + iy*sy + ix*sx
-                            const int sx = g.dstep * 8, sy = g.dstep * prow * 8, row_back = sy - g.nx * sx;
-                            const uint32_t off0 = (uint32_t)(((g.dy0 + hy0) * prow + g.dx0 + hx0) * 8);
-                            const uint32_t tmem_ds = tmem_d + (uint32_t)(sub * p.n_t);
-                            uint32_t& accumulate = sub ? accumulate1 : accumulate0;
-                            const int te = centre_only ? 1 : g.ntaps;
-                            uint32_t a_lo = a_lo0 + (centre_only ? (uint32_t)((hy0 * prow + hx0) * 8) : off0);
+                        for (int sub = 0; sub < nsub; ++sub) {        // the taps of one sub-phase against this slab's patch
+                            const int sx = sub ? sx1 : sx0, rb = sub ? rb1 : rb0, nx = sub ? nx1 : nx0;
+                            const uint32_t tmem_ds = sub ? tmem_d + (uint32_t)p.n_t : tmem_d;
+                            uint32_t accumulate = sub ? accum1 : accum0;
+                            const int te = centre_only ? 1 : (sub ? nt1 : nt0);
+                            uint32_t a_lo = a_lo0 + (centre_only ? c_off : (sub ? off1 : off0));
                             int ix = 0;
                             if (resident) {
                                 // weights stay put: slab cb's taps start at cb * gb tiles, addressed by their device tap index
                                 // (a centre-only slab keeps just that one tap, so the slabs after it start gb - 1 tiles earlier)
-                                const uint32_t r_off = (uint32_t)((second && a1c ? nch0 * gb + (cb - nch0) * p.res_c_planes : cb * gb) * b_plane_bytes);
-                                const uint32_t b_lo = desc_lo(smem_u32(smem_b) + r_off) + (centre_only ? 0u : (uint32_t)g.wi0 * b16);
+                                const uint32_t r_off = (uint32_t)((centre_only ? nch0 * gb + (cb - nch0) * p.res_c_planes : cb * gb) * b_plane_bytes);
+                                const uint32_t b_lo = desc_lo(smem_u32(smem_b) + r_off) + (centre_only ? 0u : (sub ? wi1 : wi0));
                                 if (exp_mma & 128) {}
-                                else halo_taps_terms<PAIR>(split ? (second ? terms1 : terms0) : 0, nk, te, tmem_ds, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, centre_only ? b16 : bp16, b16, sx, row_back, g.nx, ix, accumulate);
+                                else halo_taps_terms<PAIR>(tsel, nk, te, tmem_ds, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, centre_only ? b16 : bp16, b16, sx, rb, nx, ix, accumulate);
                             } else
                             for (int t0 = 0; t0 < te; t0 += gb) {
                                 const int ng = min(gb, te - t0);
@@ -732,10 +740,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                                 tc_fence_after();
                                 const uint32_t b_lo = desc_lo(smem_u32(smem_b) + (uint32_t)(sb * gb * b_bytes));
                                 if (exp_mma & 128) {}                 // timing experiment: the issue loop without the MMAs
-                                else halo_taps_terms<PAIR>(split ? (second ? terms1 : terms0) : 0, nk, ng, tmem_ds, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, g.nx, ix, accumulate);
+                                else halo_taps_terms<PAIR>(tsel, nk, ng, tmem_ds, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, rb, nx, ix, accumulate);
                                 if (PAIR) umma_commit_pair(emptyB0 + 8 * sb); else umma_commit(emptyB0 + 8 * sb);
                                 if (++sb == nb_stages) { sb = 0; pb ^= 1; }
                             }
+                            if (sub) accum1 = accumulate; else accum0 = accumulate;
                         }
                         if (PAIR) umma_commit_pair(empty0 + 8 * sa); else umma_commit(empty0 + 8 * sa);
                         if (++sa == n_stages) { sa = 0; pa ^= 1; }
@@ -795,8 +804,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                        (p.out_plane_elems & 15) == 0 && !(p.exp_flags & 512);
         // the N tile is dealt out in groups of 8 columns (16-byte fp16 stores): n_t = 80 -> 3, 3, 2, 2 groups
         const int n_t = p.n_t, n8 = n_t >> 3;
-        const int g_lo = sub * (n8 / kEpiSub) + min(sub, n8 % kEpiSub);
-        const int g_n = n8 / kEpiSub + (sub < n8 % kEpiSub ? 1 : 0);
+        // merge_px (two px phases side by side in one stage): the two warps of a lane quarter take one phase each, i.e. all
+        // n_t columns of it and the output pixel `sub` to the right; otherwise they share the columns of one phase
+        const bool px_split = nsub == 2;
+        const int g_lo = px_split ? 0 : sub * (n8 / kEpiSub) + min(sub, n8 % kEpiSub);          // first column group (channels)
+        const int g_n = px_split ? n8 : n8 / kEpiSub + (sub < n8 % kEpiSub ? 1 : 0);
+        const uint32_t col0 = (uint32_t)((px_split ? sub * n_t : 0) + g_lo * 8);                 // first TMEM column
+        const int px_off = px_split ? sub : 0;
         // x16 TMEM loads per warp, plus one x8 load for an odd group count; timing experiments: 8 = first chunk
         // only, 32 = barrier handshake only, 16 = no global stores
         const bool noepi = (p.exp_flags & 32) != 0, one_chunk = (p.exp_flags & 8) != 0;
@@ -817,7 +831,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const bool valid = n < n_tiles && !nostore;
             int oy, ox; bool writer = valid;
             if (e.pool) { oy = y >> 1; ox = x >> 1; writer = valid && !(y & 1) && !(x & 1); }
-            else if (os == 2) { oy = 2 * y + (nsub == 2 ? t.phase : (t.phase >> 1)); ox = 2 * x + (nsub == 2 ? 0 : (t.phase & 1)); }
+            else if (os == 2) { oy = 2 * y + (px_split ? t.phase : (t.phase >> 1)); ox = 2 * x + (px_split ? px_off : (t.phase & 1)); }
             else { oy = y; ox = x; }
             const int64_t opix = ((int64_t)n * oh_ + oy) * ow_ + ox;
             const int co0 = t.n_idx * n_t + g_lo * 8;              // first output channel of this warp's columns
@@ -830,9 +844,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             mbar_wait_relaxed(tfull0 + 8 * acc, acc_phase);
             clk.lap(c_wt);
             tc_fence_after();
-          for (int sp = 0; sp < nsub; ++sp) {        // merge_px: the second half of the stage holds the px = 1 phase -> the pixel one to the right
-            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride) + (uint32_t)(sp * n_t + g_lo * 8);
-            if (sp) { of += e.cout; oh += e.out_cs; }
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride) + col0;
             // the TMEM load of the next chunk is in flight while the current one is processed; an odd first group is
             // taken alone so that every 16-column chunk starts on a 32-byte boundary of the fp16 row (256-bit stores)
             uint32_t ra[16], rb[16], rt[8];
@@ -864,7 +876,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 epi_chunk<8, SKIPC, TOPK>(p, e, rt, cb16 + n_full * 16, xs, writer, of16 + n_full * 16, oh16 + n_full * 16, z);
                 __syncwarp();
             }
-          }
             if (TOPK > 0) {
                 // the warps of a lane quarter hold the column shares of each pixel: combine the partial logits
                 float4* zs = reinterpret_cast<float4*>(s_z) + (acc * (kEpiSub - 1) * 128 + m);
