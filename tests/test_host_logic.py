@@ -126,6 +126,25 @@ def test_probe_tiles_equal_the_oracle_tiler(sample_raw):
         assert np.abs(got - want).max() <= (0 if f == 1.0 else 1e-6)
 
 
+def test_precision_knapsack_over_correction_terms():
+    """engine.choose_op_terms: one option per op (terms, error alone, time), fastest assignment whose errors fit the budget
+    in quadrature; engine.tensor_op_sources: the K each concat source contributes (weights of its correction MMAs)."""
+    from unmicst_b200 import modelzoo
+    from unmicst_b200.engine import choose_op_terms, tensor_op_sources
+    opts = {1: [(0, 1e-3, 1.0), (10, 5e-4, 1.5), (15, 0.0, 3.0)], 2: [(0, 2e-4, 1.0), (15, 0.0, 3.0)],
+            3: [(0, 9e-4, 2.0), (2, 3e-4, 3.0), (15, 0.0, 6.0)]}
+    assert choose_op_terms(opts, 1e-3) == {1: 10, 2: 0, 3: 2}          # 5e-4, 2e-4, 3e-4 -> 6.2e-4, time 5.5
+    assert choose_op_terms(opts, 1e-5) == {1: 15, 2: 15, 3: 15}
+    assert choose_op_terms(opts, 1.0) == {1: 0, 2: 0, 3: 0}
+    assert choose_op_terms(opts, 6e-4) == {1: 15, 2: 0, 3: 2}
+    with pytest.raises(ValueError):
+        choose_op_terms({1: [(0, 1e-3, 1.0)]}, 1e-4)                    # no zero-error option, nothing fits
+    src = {n: ks for _, n, ks in tensor_op_sources(modelzoo.synthetic_model("nucleiDAPI1-5"))}
+    assert src["lu1.conv2"] == [9 * 80, 9 * 160] and src["lu0.conv2"] == [9 * 80, 9] and src["ld1.conv0"] == [9 * 80]
+    legacy = {n: ks for _, n, ks in tensor_op_sources(modelzoo.synthetic_model("nucleiDAPI"))}
+    assert legacy["ld0.conv1"] == [25 * 16]                            # its one-channel shortcut lives in the epilogue, not in K
+
+
 def test_error_budgeted_layer_selection():
     """engine.choose_single_mask: the subset with the largest saving whose errors, added in quadrature, fit the budget."""
     from unmicst_b200.engine import choose_single_mask

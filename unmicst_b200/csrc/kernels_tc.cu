@@ -512,7 +512,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int m_units = (m_tiles + per_unit - 1) / per_unit;
     // conv-transpose with merge_px: a work item covers the two sub-pixel phases (px = 0, 1) of one output row parity;
     // they share every input patch and fill two n_t-column halves of one accumulator stage
-    const int nsub = p.merge_px ? 2 : 1;
+    const int nsub = (TOPK == 0 && SKIPC == 0 && p.merge_px) ? 2 : 1;      // (never set for the fused-lt / shortcut variants: keeps them lean)
     const int total = (p.nphase / nsub) * m_units * p.n_ntiles;
     const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int item_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;

@@ -618,7 +618,7 @@ int lower_conv_tc(umx_handle* h, Op& op) {
         }
         {
             const char* e = getenv("UMX_TC_MERGE_PX");
-            tp.merge_px = (tp.halo && sp.transpose && tp.nphase == 4 && 2 * tp.n_t <= 256 && (e ? atoi(e) : 1)) ? 1 : 0;
+            tp.merge_px = (tp.halo && sp.transpose && tp.nphase == 4 && 2 * tp.n_t <= 256 && !narrow && op.fuse_top < 0 && (e ? atoi(e) : 1)) ? 1 : 0;
         }
         tp.kslab = 1;
         if (!tp.halo) {
