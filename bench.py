@@ -55,7 +55,7 @@ WORKLOADS = {
     "sample105": dict(model="nucleiDAPI", H=832, W=960, planes=1, scale=1.0, cfg="configs[0] sample image 105.tif, legacy graph, real checkpoint", file=SAMPLE_TIF),
     "solo105": dict(model="nucleiDAPI1-5", H=832, W=960, planes=1, scale=1.0, cfg="configs[0] sample image 105.tif, unmicst-solo graph", file=SAMPLE_TIF),
 }
-DEFAULT_CONFIGS = ["sample105", "solo105", "duo4k", "solo40k", "cyto2tma"]
+DEFAULT_CONFIGS = ["sample105", "solo105", "duo4k", "solo40k", "cyto2tma", "cyto2cores"]
 
 
 def synthetic_dna(H: int, W: int, seed: int = 1234, lamin: bool = False) -> np.ndarray:
@@ -332,6 +332,7 @@ def run_workload(name: str, args, steps: int, warmup: int, main: bool, reuse=Non
     # ---- rank 0 picks the weights' steepness and the arithmetic; every rank then builds the identical engine
     plan = None
     if rank == 0:
+      try:
         host_threads(world)
         if reuse and reuse.get("model_name") == model_name:
             model, gain, prec, terms, auto = reuse["model"], reuse["gain"], reuse["prec"], reuse["terms"], reuse["auto"]
@@ -344,7 +345,11 @@ def run_workload(name: str, args, steps: int, warmup: int, main: bool, reuse=Non
             elif prec == "default":
                 prec = "split3"
         plan = dict(gain=gain, prec=prec, terms=terms)
+      except Exception as ex:              # every rank must leave this workload together
+        plan = {"error": f"{type(ex).__name__}: {ex}"[:300]}
     plan = bcast(plan, world)
+    if "error" in plan:
+        raise RuntimeError(plan["error"])
     if rank != 0:
         from unmicst_b200 import modelzoo
         d = os.path.join(ROOT, "tests", "golden", "models", model_name)
@@ -355,8 +360,9 @@ def run_workload(name: str, args, steps: int, warmup: int, main: bool, reuse=Non
     K = eng.K
 
     # ---- parity of the timed engine against the oracle on tiles of this image
-    parity = None
+    parity, want = None, None
     if rank == 0:
+      try:
         taps = {}
         want = oracle_forward(model, taps)(probe)
         got = eng.forward_tiles(probe)
@@ -365,6 +371,9 @@ def run_workload(name: str, args, steps: int, warmup: int, main: bool, reuse=Non
                   "max_abs_logit": float(np.abs(taps["logits"]).max()), "tolerance": 2e-3, "argmax_required": 0.999,
                   "within_contract": bool(np.abs(got - want).max() <= 2e-3 and (got.argmax(-1) == want.argmax(-1)).mean() >= 0.999),
                   "auto": auto}
+      except Exception as ex:              # rank-0-only work must not strand the other ranks at the next barrier
+        parity = {"error": f"{type(ex).__name__}: {ex}"[:300], "max_abs_dp": None, "argmax_agreement": None, "max_abs_logit": None,
+                  "within_contract": None, "auto": auto}
 
     _, sub, npr, npc = tile_geometry(IH, IW, S)
     bands = split_tile_rows(npr, world)
@@ -446,8 +455,11 @@ def run_workload(name: str, args, steps: int, warmup: int, main: bool, reuse=Non
     # ---- stitched uint8: crop of the timed (resident) output vs the oracle pipeline
     crop_check = None
     if rank == 0 and args.crop_check:
-        crop_check = stitched_crop_check(model, img, premap, scale, lambda v: d_out[:, :v, :v].cpu().numpy(),
-                                         rows_available=r1 if world > 1 else 0)
+        try:
+            crop_check = stitched_crop_check(model, img, premap, scale, lambda v: d_out[:, :v, :v].cpu().numpy(),
+                                             rows_available=r1 if world > 1 else 0)
+        except Exception as ex:
+            crop_check = {"error": f"{type(ex).__name__}: {ex}"[:300]}
 
     # ---- multi-GPU: every band of the e2e output, bit for bit, against ONE GPU doing the whole slide
     bands_ok = None
@@ -528,7 +540,7 @@ def run_workload(name: str, args, steps: int, warmup: int, main: bool, reuse=Non
             fn()
             t_ms = timed(fn, 2)[0] / 2
             entry = {"value": IH * IW / 1e6 / (t_ms / 1e3), "ms_per_step": t_ms}
-            if rank == 0:
+            if rank == 0 and want is not None:
                 g2 = e2.forward_tiles(probe)
                 entry["max_abs_dp_vs_oracle"] = float(np.abs(g2 - want).max())
             modes[mode] = entry
@@ -560,7 +572,7 @@ def run_workload(name: str, args, steps: int, warmup: int, main: bool, reuse=Non
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {"workload": cfg, "model": model_name,
-                       "weights": (f"synthetic seed 0, last linear map x{gain:.2f} so that max|logit| = {parity['max_abs_logit']:.1f} on this image "
+                       "weights": (f"synthetic seed 0, last linear map x{gain:.2f} so that max|logit| = {parity['max_abs_logit'] or float('nan'):.1f} on this image "
                                    "(real checkpoint not shipped)") if gain is not None else "real checkpoint (tests/golden/models)",
                        "H": IH, "W": IW, "raw_H": H, "raw_W": W, "scaling_factor": scale, "tiles": npr * npc, "tile": S,
                        "precision": prec, "precision_requested": args.precision,
@@ -590,6 +602,56 @@ def run_workload(name: str, args, steps: int, warmup: int, main: bool, reuse=Non
     return out, ctx, img
 
 
+def run_cores(args, reuse):
+    """configs[4] as the reference's batch script sees it (batchUNet2DTMACycif.py:539-569): 60 separate TMA cores of
+    3072 x 3072 px, here through umx_infer_images (tiles of several cores share every network launch), cores dealt
+    round-robin to the ranks.  Host buffers in and out: the number is end to end."""
+    import torch
+    from unmicst_b200 import modelzoo
+    from unmicst_b200.engine import Engine, PreMap
+    rank, world, local = dist_env()
+    n_cores, side, distinct = 60, 3072, 4
+    plan = bcast(dict(gain=reuse["gain"], prec=reuse["prec"], terms=reuse["terms"]) if rank == 0 else None, world)
+    model = reuse["model"] if rank == 0 else modelzoo.synthetic_model("CytoplasmIncell2", seed=0, logit_gain=plan["gain"])
+    base = [synthetic_dna(side, side, seed=100 + i) for i in range(distinct)]
+    mine = [base[i % distinct] for i in range(rank, n_cores, world)]
+    pms = [PreMap(in_scale=1.0 / 65535, rescale=True, imin=float(c.min()) / 65535, imax=float(c.max()) / 65535) for c in mine]
+    eng = Engine(model, device=local, precision=plan["prec"], max_batch_tiles=args.max_batch, op_terms=plan["terms"])
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng.infer_images(mine[:2], pms[:2])                       # warm-up
+    n0 = eng.launch_count
+    barrier()
+    t0 = time.perf_counter()
+    outs = eng.infer_images(mine, pms)
+    own = time.perf_counter() - t0
+    barrier()
+    launches = eng.launch_count - n0
+    secs = max(gather_objs(own, world))
+    same = None
+    if rank == 0:
+        one, _ = eng.infer_image(mine[0], premap=pms[0])
+        same = bool(np.array_equal(one, outs[0]))
+    eng.close()
+    if rank != 0:
+        return None
+    S = model.hp["imSize"]
+    sub = S - 2 * (S // 8)
+    tiles_per_core = (-(-side // sub)) ** 2
+    return {"workload": "configs[4] as 60 separate 3072 x 3072 TMA cores through umx_infer_images (many images per launch), end to end from host buffers",
+            "model": "CytoplasmIncell2", "n_gpus": world, "precision": plan["prec"], "cores": n_cores, "tiles_per_core": tiles_per_core,
+            "e2e": {"value": n_cores * side * side / 1e6 / secs, "unit": "MP/s", "seconds": secs,
+                    "h2d_bytes_per_step": n_cores * side * side * 2, "d2h_bytes_per_step": n_cores * side * side * model.hp["nClasses"]},
+            "value": n_cores * side * side / 1e6 / secs, "unit": "MP/s",
+            "gpu_launches_rank0": launches,
+            "equals_single_image_call_bit_for_bit": same}
+
+
 def compact(o):
     r = o["roofline"]
     return {"workload": o["config"]["workload"], "model": o["config"]["model"], "weights": o["config"]["weights"],
@@ -611,18 +673,33 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     out, ctx, img = run_workload(args.workload, args, args.steps, args.warmup, main=True)
     if rank == 0 and args.cpu_budget > 0:
-        wl = WORKLOADS[args.workload]
-        n_side = tiles_side_for_budget(ctx["model"], args.cpu_budget)
-        out["cpu_baseline"] = cpu_baseline(ctx["model"], img, wl["scale"], n_side)
+        try:
+            wl = WORKLOADS[args.workload]
+            n_side = tiles_side_for_budget(ctx["model"], args.cpu_budget)
+            out["cpu_baseline"] = cpu_baseline(ctx["model"], img, wl["scale"], n_side)
+        except Exception as ex:
+            out["cpu_baseline"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
     del img
     names = [] if args.configs == "none" else (DEFAULT_CONFIGS if args.configs == "all" else args.configs.split(","))
     configs = []
+    cyto_ctx = None
     for name in names:
-        if name == args.workload or name not in WORKLOADS:
+        if name == args.workload or (name not in WORKLOADS and name != "cyto2cores"):
             continue
         t0 = time.perf_counter()
         try:
-            o, _, _ = run_workload(name, args, max(1, min(3, args.steps)), 1, main=False, reuse=ctx)
+            if name == "cyto2cores":
+                have = bcast(cyto_ctx is not None if rank == 0 else None, world)
+                if not have:
+                    continue                                  # needs the calibration of the cyto2tma entry
+                c = run_cores(args, cyto_ctx)
+                if rank == 0:
+                    c["wall_s"] = round(time.perf_counter() - t0, 1)
+                    configs.append(c)
+                continue
+            o, c_ctx, _ = run_workload(name, args, max(1, min(3, args.steps)), 1, main=False, reuse=ctx)
+            if name == "cyto2tma":
+                cyto_ctx = c_ctx
             if rank == 0:
                 c = compact(o)
                 c["wall_s"] = round(time.perf_counter() - t0, 1)

@@ -12,7 +12,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle import pi2d_oracle
-from unmicst_b200.engine import band_rows_py, split_tile_rows, tile_geometry
+from unmicst_b200.engine import _resize_window, band_out_rows_py, band_rows_py, split_tile_rows, tile_geometry
 
 S = 64
 H, W = 333, 250
@@ -95,3 +95,25 @@ def test_band_rows_partition_every_split(H_, S_):
         rows = [band_rows_py(H_, S_, b) for b in bands]
         assert rows[0][0] == 0 and rows[-1][1] == H_
         assert all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+
+
+@pytest.mark.parametrize("raw_h,infer_h,S_", [(20000, 40000, 64), (4000, 2000, 64), (832, 1248, 128), (1000, 370, 64), (3072, 3072, 256)])
+def test_resized_band_rows_partition_and_stay_inside_the_band(raw_h, infer_h, S_):
+    """--scalingFactor with several GPUs: a band owns the raw-grid rows whose resize window (bilinear taps + Gaussian on
+    shrink) lies inside the inference rows the band has: its own rows plus the halo above that the recomputed seam
+    tile row completes.  Bands must tile the raw rows and never look below what they emit."""
+    m, sub, npr, _ = tile_geometry(infer_h, 1, S_)
+    for parts in (1, 2, 3, 8):
+        bands = split_tile_rows(npr, parts)
+        rows = [band_out_rows_py(infer_h, raw_h, S_, b) for b in bands]
+        assert rows[0][0] == 0 and rows[-1][1] == raw_h
+        assert all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+        for (ta, tb), (r0, r1) in zip(bands, rows):
+            if r1 <= r0:
+                continue
+            have_lo = 0 if ta == 0 else (ta - 1) * sub + m               # rows completed by tile rows >= ta - 1
+            have_hi = infer_h if tb == npr else tb * sub - m
+            lo = min(_resize_window(y, infer_h, raw_h)[0] for y in (r0, r1 - 1))
+            hi = max(_resize_window(y, infer_h, raw_h)[1] for y in (r0, r1 - 1))
+            assert lo >= have_lo or ta == 0
+            assert hi < have_hi or tb == npr

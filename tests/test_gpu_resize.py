@@ -97,6 +97,16 @@ def test_bands_with_scaling_reassemble_bit_exactly(sample_raw, solo):
             assert np.array_equal(out, whole)
 
 
+def test_band_out_rows_python_twin(solo):
+    from unmicst_b200.engine import band_out_rows_py, split_tile_rows, tile_geometry
+    with _engine(solo) as e:
+        for raw_h, infer_h in ((300, 600), (1000, 370), (500, 500), (4000, 2000)):
+            _, _, npr, _ = tile_geometry(infer_h, 1, 64)
+            for parts in (1, 3, 8):
+                for band in split_tile_rows(npr, parts):
+                    assert e.band_out_rows(infer_h, raw_h, band) == band_out_rows_py(infer_h, raw_h, 64, band)
+
+
 @pytest.mark.parametrize("scaled", [False, True])
 def test_streamed_bands_equal_one_call(sample_raw, solo, scaled):
     """stream_image: bands continue each other on the device (UMX_F_CONTINUE), nothing recomputed, same bytes."""

@@ -72,10 +72,13 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
 // roles 5-15 % on the issue-bound layers and, as an ABI call, 5 MB of code.
 constexpr uint32_t kSpinLimit = 1u << 22;
 __device__ __forceinline__ void mbar_timed_out(uint32_t bar, uint32_t parity) {
-    // one line per stuck warp is enough to read the pipeline state: warp 0 = TMA producer, warp 1 = MMA issuer, 2.. = epilogue
+#ifdef UMX_TC_DEBUG     // which barrier each role is stuck on (warp 0 = TMA producer, 1 = MMA issuer, 2.. = epilogue); UMX_TC_EXP=2048 prints the layout
     if ((threadIdx.x & 31) == 0 || threadIdx.x < 64)
         printf("umx tc_conv: mbarrier wait timed out (block %d warp %d thread %d, barrier at shared 0x%x, parity %u)\n",
                blockIdx.x, threadIdx.x >> 5, threadIdx.x, bar, parity);
+#else                   // (kept to two arguments: every wait site inlines this call's argument buffer)
+    printf("umx tc_conv: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+#endif
     __trap();
 }
 template <uint32_t HINT_NS>

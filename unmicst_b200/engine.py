@@ -93,6 +93,42 @@ def band_rows_py(H: int, S: int, tile_rows: Tuple[int, int]) -> Tuple[int, int]:
     return min(H, max(0, p0 - m)), min(H, max(0, p1 - m))
 
 
+def _resize_window(y: int, src: int, dst: int) -> Tuple[int, int]:
+    """First / last source row the resize of destination row y touches (skimage.transform.resize: bilinear on the half-pixel
+    grid, Gaussian of radius int(4 sigma + 0.5), sigma = (src/dst - 1)/2, when shrinking) — before mirroring."""
+    if src == dst:
+        return y, y
+    zoom = src / dst
+    r = int(4.0 * max(0.0, (zoom - 1.0) / 2.0) + 0.5) if dst < src else 0
+    cc = abs((y + 0.5) * zoom - 0.5)
+    s0 = int(np.floor(cc))
+    return s0 - r, s0 + 1 + r
+
+
+def band_out_rows_py(infer_h: int, raw_h: int, S: int, tile_rows: Tuple[int, int]) -> Tuple[int, int]:
+    """Pure-Python twin of umx_band_out_rows: raw-grid rows [r0, r1) a tile-row band writes when the network runs at
+    ``infer_h`` rows and the pages are resized back to ``raw_h`` rows.  The cut between two bands is the first raw row
+    whose resize window reaches the inference rows the upper band does not emit."""
+    if raw_h == infer_h:
+        return band_rows_py(infer_h, S, tile_rows)
+    m, sub, npr, _ = tile_geometry(infer_h, 1, S)
+    a, b = tile_rows
+    b = npr if b <= 0 or b > npr else b
+
+    def cut(t: int) -> int:
+        if t <= 0:
+            return 0
+        if t >= npr:
+            return raw_h
+        bound = t * sub - m
+        y = 0
+        while y < raw_h and _resize_window(y, infer_h, raw_h)[1] < bound:
+            y += 1
+        return y
+
+    return cut(a), cut(b)
+
+
 AUTO_TOLERANCE = 1e-3     # max|dp| budget of the chosen mode vs split3 on the probe tiles: half of the 2e-3 contract
 AUTO_PROBE_TILES = 64     # probe tiles sampled from the image being processed (corners, edges, interior)
 
