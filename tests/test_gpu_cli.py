@@ -174,7 +174,7 @@ def test_multi_gpu_auto_and_scaling_match_single_gpu(sample_raw):
     me = MultiEngine(m, [0, 1], "auto", probe_tiles=tiles)
     try:
         two, _ = me.infer_image(crop, premap=pm, infer_shape=shape, cli_quant=True)
-        with Engine(m, 0, me.precision, single_mask=me.single_mask) as e:
+        with Engine(m, 0, me.precision, op_terms=me.op_terms) as e:
             one, _ = e.infer_image(crop, premap=pm, infer_shape=shape, cli_quant=True)
     finally:
         me.close()
