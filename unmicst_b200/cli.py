@@ -104,9 +104,12 @@ def split_name(file_name: str, proper: bool):
 def read_channel(path: str, file_type: str, channel: int) -> np.ndarray:
     if file_type in ("ome.tif", "ome.tiff", "btf", "tif", "tiff"):
         return tiffio.read_page(path, int(channel))
-    if file_type in ("czi", "nd2"):
-        raise NotImplementedError(f".{file_type} needs the czifile / nd2reader packages, which this build does not bundle; "
-                                  f"convert to (OME-)TIFF")
+    if file_type == "czi":                    # czifile.CziFile(...).asarray()[0, 0, channel, 0, 0, :, :, 0]  (UnMicst1-5.py:797-800)
+        from . import czi
+        return czi.read_channel(path, int(channel))
+    if file_type == "nd2":
+        raise NotImplementedError(".nd2 needs the nd2reader package (Nikon's container is not published), which this build does "
+                                  "not bundle; convert to (OME-)TIFF")
     raise NotImplementedError(f"Don't know how to read image with extension .{file_type}")
 
 
