@@ -116,6 +116,9 @@ typedef struct umx_opts {
                              /* BigTIFF writer, UnMicst1-5.py:852-862) at no extra cost                                      */
 #define UMX_F_STITCH_REPLACE 16 /* PI2D mode 'replace' (PartitionOfImage.py:99-100): in overlaps the tile patched last (row-major order) */
                                 /* wins and no ramp weights are applied; default is 'accumulate' (:95-98, what the CLI uses)           */
+#define UMX_F_FP16_QUANT 32  /* first quantisation exactly as the reference evaluates it: PI2D returns float16, so               */
+                             /* np.uint8(255 * PM) (UnMicst1-5.py:848) is floor(fp16(255 * fp16(p))): p >= 0.99976 gives 255 (the  */
+                             /* default, floor(255 * p) in fp32, gives 254 there); the fp16 ACCUMULATION of PI2D is not emulated  */
 #define UMX_F_CLI_QUANT  2   /* out_u8 = the page the reference CLI writes (UnMicst1-5.py:848-853): uint8(255*p), resize back */
                              /* to the H x W grid of img when infer_h/infer_w differ, then uint8(255*x) a second time;       */
                              /* out_u8 is then [K][H][W] (rows of umx_band_out_rows for a band); out_f32 must be NULL        */

@@ -203,3 +203,19 @@ def test_precision_override_is_refused_not_ignored(solo):
             e.forward_tiles(tiles, precision="fp32")
         with pytest.raises(EngineError):
             e.infer_image(rng.random((70, 70)), precision="single")
+
+
+def test_reference_float16_quantisation_rule(solo):
+    """UMX_F_FP16_QUANT: np.uint8(255 * PM) with PM float16 as PI2D returns it (UnMicst1-5.py:848): the
+    kernel's rule equals numpy's on the very same probabilities, saturates to 255 where the default gives 254, and
+    never differs from the default by more than one level."""
+    rng = np.random.default_rng(13)
+    img = rng.random((200, 140))
+    with _engine(solo) as e:
+        u8, f32 = e.infer_image(img, want_f32=True)
+        r16, _ = e.infer_image(img, fp16_quant=True)
+    assert np.array_equal(r16, np.uint8(255 * f32.astype(np.float16)))
+    assert np.array_equal(u8, np.uint8(255 * f32.astype(np.float64)))
+    assert np.abs(r16.astype(int) - u8.astype(int)).max() <= 1
+    want16 = pi2d_oracle.quantize_u8(pi2d_oracle.infer_image(img, _fw(solo), 64, 1, solo.mean, solo.std, 32, accum_dtype=np.float16))
+    assert np.abs(r16.astype(int) - want16.astype(int)).max() <= 1

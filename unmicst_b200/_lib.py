@@ -21,6 +21,7 @@ UMX_F_CLI_QUANT = 2
 UMX_F_PREMAP_PER_PLANE = 4
 UMX_F_CONTINUE = 8
 UMX_F_STITCH_REPLACE = 16
+UMX_F_FP16_QUANT = 32
 
 PRECISIONS = {"default": UMX_PREC_DEFAULT, "fp32": UMX_PREC_FP32, "split3": UMX_PREC_SPLIT3, "single": UMX_PREC_SINGLE,
               "mixed": UMX_PREC_MIXED}

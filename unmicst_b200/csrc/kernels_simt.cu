@@ -682,7 +682,11 @@ __global__ void __launch_bounds__(256) stitch_kernel(const StitchParams p) {
         const float v = num[k] / cnt;
         if (p.out_f32) p.out_f32[k * p.out_plane_stride + o] = v;
         if (p.out_u8) {
-            uint8_t q = (uint8_t)fminf(255.f, floorf(255.f * v));
+            uint8_t q;
+            if (p.fp16_quant) {     // p rounded to float16 (PI2D's output dtype), 255 * p rounded to float16 again, then truncated
+                const float p16 = __half2float(__float2half_rn(v));
+                q = (uint8_t)fminf(255.f, floorf(__half2float(__float2half_rn(255.f * p16))));
+            } else q = (uint8_t)fminf(255.f, floorf(255.f * v));
             if (p.requant) q = (uint8_t)(__dmul_rn(255.0, __dmul_rn((double)q, 1.0 / 255)));      // second quantisation at equal size
             p.out_u8[k * p.out_plane_stride + o] = q;
         }

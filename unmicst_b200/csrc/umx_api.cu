@@ -1447,6 +1447,7 @@ int umx_infer_image(umx_handle* h, const void* img, int32_t dtype, int32_t n_pla
             sp.row0 = r0; sp.row1 = r1;
             sp.requant = (cli_quant && !resize_back) ? 1 : 0;
             sp.replace = (opts && (opts->flags & UMX_F_STITCH_REPLACE)) ? 1 : 0;
+            sp.fp16_quant = (opts && (opts->flags & UMX_F_FP16_QUANT)) ? 1 : 0;
             const bool staged = !resize_back && (out_u8 ? !u8_direct : !f32_direct);
             if (resize_back) {
                 sp.out_u8 = h->d_band_u8; sp.out_plane_stride = (int64_t)(E1 - E0) * IW; sp.out_row_base = E0;

@@ -167,6 +167,7 @@ struct StitchParams {           // PI2D.patchOutput/getValidOutput as a gather +
     int64_t  out_plane_stride;  // elements between class planes
     int32_t  out_row_base;
     int32_t  replace;           // 1: PI2D 'replace' mode (PartitionOfImage.py:99-100): the last tile written over a pixel wins, no weights
+    int32_t  fp16_quant;        // 1: first quantisation as the reference evaluates it, np.uint8(255 * <float16 array>) (UnMicst1-5.py:848)
     int32_t  requant;           // 1: out_u8 = uint8(255 * (uint8(255 p) * (1/255))), the reference's second quantisation at equal size (UnMicst1-5.py:850-853)
 };
 

@@ -610,7 +610,7 @@ class Engine:
                   tile_rows: Optional[Tuple[int, int]] = None, premap: Optional[PreMap] = None,
                   out_plane_stride: int = 0, out_row_base: int = 0, precision: str = "default",
                   no_sync: bool = False, infer_shape: Optional[Tuple[int, int]] = None, cli_quant: bool = False,
-                  continue_prev: bool = False, stitch_mode: str = "accumulate") -> None:
+                  continue_prev: bool = False, stitch_mode: str = "accumulate", fp16_quant: bool = False) -> None:
         """Raw-pointer form (host pageable / pinned or device memory — the library detects which).
         ``infer_shape``: run the network on the image resized to this (rows, cols) (--scalingFactor);
         ``cli_quant``: out_u8 = the page the reference CLI writes ([K,H,W] of the raw grid, quantised twice)."""
@@ -619,7 +619,8 @@ class Engine:
             o.tile_row0, o.tile_row1 = int(tile_rows[0]), int(tile_rows[1])
         o.precision = _lib.PRECISIONS[precision]
         o.flags = ((_lib.UMX_F_NO_SYNC if no_sync else 0) | (_lib.UMX_F_CLI_QUANT if cli_quant else 0) |
-                   (_lib.UMX_F_CONTINUE if continue_prev else 0) | (_lib.UMX_F_STITCH_REPLACE if stitch_mode == "replace" else 0))
+                   (_lib.UMX_F_CONTINUE if continue_prev else 0) | (_lib.UMX_F_STITCH_REPLACE if stitch_mode == "replace" else 0) |
+                   (_lib.UMX_F_FP16_QUANT if fp16_quant else 0))
         if stitch_mode not in ("accumulate", "replace"):
             raise ValueError("stitch_mode must be 'accumulate' or 'replace' (PartitionOfImage.py:92-100)")
         if infer_shape is not None:
@@ -643,8 +644,10 @@ class Engine:
                     premap: Optional[PreMap] = None, want_u8: bool = True, want_f32: bool = False,
                     tile_rows: Optional[Tuple[int, int]] = None, out_u8: Optional[np.ndarray] = None,
                     out_f32: Optional[np.ndarray] = None, precision: str = "default",
-                    infer_shape: Optional[Tuple[int, int]] = None, cli_quant: bool = False, stitch_mode: str = "accumulate"):
+                    infer_shape: Optional[Tuple[int, int]] = None, cli_quant: bool = False, stitch_mode: str = "accumulate",
+                    fp16_quant: bool = False):
         """image [H,W] or [C,H,W] (uint8/uint16/float32/float64) -> (u8 [K,h,w] | None, f32 [K,h,w] | None).
+        ``fp16_quant``: quantise as the reference's float16 pipeline does (np.uint8(255 * float16), UMX_F_FP16_QUANT).
 
         With ``tile_rows`` only the image rows of that band are written (into full-size outputs).
         ``infer_shape`` = (rows, cols) the network runs at (the image is resized on the GPU with
@@ -672,7 +675,7 @@ class Engine:
                        out_u8.ctypes.data if out_u8 is not None else 0,
                        out_f32.ctypes.data if out_f32 is not None else 0,
                        tile_rows=tile_rows, premap=premap, precision=precision, infer_shape=infer_shape, cli_quant=cli_quant,
-                       stitch_mode=stitch_mode)
+                       stitch_mode=stitch_mode, fp16_quant=fp16_quant)
         return out_u8, out_f32
 
     def stream_image(self, image: np.ndarray, mean: Optional[float] = None, std: Optional[float] = None,
