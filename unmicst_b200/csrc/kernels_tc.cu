@@ -89,6 +89,15 @@ __device__ __forceinline__ void mbar_wait_impl(uint32_t bar, uint32_t parity) {
     }
 }
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) { mbar_wait_impl<20000u>(bar, parity); }
+// epilogue wait with back-off: the hinted try_wait returns every ~70 ns in practice, so eight waiting warps would spend
+// their time (and a third of the SM's issued instructions) polling; after a few failed polls they nap between polls
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, uint32_t nap_ns) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+        if (++spins > kSpinLimit) mbar_timed_out(bar, parity);
+        if (spins > 4) __nanosleep(nap_ns);
+    }
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { mbar_wait_impl<100000u>(bar, parity); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -821,6 +830,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int n_full = noepi ? 0 : (one_chunk ? min(1, g_n >> 1) : ((g_n - lead8) >> 1));
         const bool tail8 = ((g_n - lead8) & 1) && !noepi && !one_chunk;
         const bool nostore = (p.exp_flags & 16) != 0;
+        const uint32_t nap_ns = p.epi_nap_ns;
         const int in_h = p.in_h, in_w = p.in_w, os = p.os, n_tiles = p.n_tiles;
         const int m = q * 32 + lane;
         const int xl = m % p.bw;
@@ -844,7 +854,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             if (SKIPC > 0 && valid) xs = __ldg(p.skip_src + ((int64_t)n * in_h + y) * in_w + x);
             float z[4] = {0.f, 0.f, 0.f, 0.f};           // fused lt logits
             clk.lap(c_work);
-            mbar_wait_relaxed(tfull0 + 8 * acc, acc_phase);
+            if (nap_ns) mbar_wait_backoff(tfull0 + 8 * acc, acc_phase, nap_ns); else mbar_wait_relaxed(tfull0 + 8 * acc, acc_phase);
             clk.lap(c_wt);
             tc_fence_after();
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride) + col0;

@@ -631,6 +631,8 @@ int lower_conv_tc(umx_handle* h, Op& op) {
         }
     }
     if (const char* e = getenv("UMX_TC_EXP")) tp.exp_flags = atoi(e);
+    tp.epi_nap_ns = 0;
+    if (const char* e = getenv("UMX_TC_NAP")) tp.epi_nap_ns = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("UMX_TC_STAGES")) {
         const int cap = std::max(2, atoi(e));
         if (tp.halo) { if (!tp.b_resident) tp.b_stages = std::min(tp.b_stages, cap); } else tp.stages = std::min(tp.stages, cap);

@@ -41,6 +41,7 @@ struct TcConvParams {
     int32_t res_c_planes;        // resident mode: weight planes a centre-only (1x1 term) slab keeps: 1 = hi, 2 = hi + lo (its a_hi*w_lo term is on)
     int32_t b_resident;          // halo mode: every (slab, tap) weight tile of the layer stays in shared memory (one slot of gb = all taps per slab)
     int32_t kslab;               // plain mode: 64-channel slabs per ring slot (more MMAs per barrier round trip)
+    uint32_t epi_nap_ns;         // epilogue warps nap this long between polls of the accumulator-ready barrier (0: hinted try_wait only)
     int32_t exp_flags;           // timing experiments only (results invalid): 1 no TMA loads, 4 one MMA per slab, 8 first epilogue chunk only, 16 no global stores, 32 no epilogue work
     unsigned long long* dbg;     // exp_flags & 64: 16 cycle counters (producer / MMA / epilogue waits and work), else nullptr
     int32_t pair;                // 1: CTA pairs, tcgen05.mma.cta_group::2 (M = 256 across two SMs)
