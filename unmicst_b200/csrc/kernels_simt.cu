@@ -259,6 +259,29 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const FirstParams p) {
     const int n = blockIdx.x / (nb * nb);
     const int rb = blockIdx.x % (nb * nb);
     const int y0 = (rb / nb) * 32, x0 = (rb % nb) * 32;
+    if (p.im.lut) {
+        // PI2D.getPatch + (x - mean)/std straight from the image: tile t = (ti, tj) covers frame rows ti*sub .. +S, the
+        // frame is the image at offset (margin, margin) and 0 (-> lut[n_codes]) elsewhere; outside the TILE the conv pads 0
+        const int t = p.im.tile0 + n, ti = t / p.im.npc, tj = t - ti * p.im.npc;
+        const int n_codes = p.im.dtype == UMX_U8 ? 256 : 65536;
+        for (int i = threadIdx.x; i < PW * PW; i += 256) {
+            const int r = i / PW, c = i % PW;
+            const int gy = y0 + r - R, gx = x0 + c - R;
+            const bool inb = gy >= 0 && gy < p.S && gx >= 0 && gx < p.S;
+            const int ir = ti * p.im.sub + gy - p.im.margin, ic = tj * p.im.sub + gx - p.im.margin;
+            const bool inside = inb && ir >= 0 && ir < p.im.H && ic >= 0 && ic < p.im.W;
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) {
+                int code = n_codes;
+                if (inside) {
+                    const int64_t idx = (int64_t)(p.im.n_planes == 1 ? 0 : ci) * p.im.plane_stride + (int64_t)(ir - p.im.img_row0) * p.im.W + ic;
+                    code = p.im.dtype == UMX_U8 ? (int)__ldg(reinterpret_cast<const uint8_t*>(p.im.img) + idx)
+                                                : (int)__ldg(reinterpret_cast<const uint16_t*>(p.im.img) + idx);
+                }
+                xin[i * CIN + ci] = inb ? __ldg(p.im.lut + ci * 65537 + code) : 0.f;
+            }
+        }
+    } else
     for (int i = threadIdx.x; i < PW * PW; i += 256) {
         const int r = i / PW, c = i % PW;
         const int gy = y0 + r - R, gx = x0 + c - R;
@@ -309,31 +332,38 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const FirstParams p) {
     }
     const int oh = p.pool ? p.S / 2 : p.S;
     for (int cg = 0; cg < cpad; cg += 16) {
-        float acc[4][16];
+        // packed fp32 FMAs (FFMA2, sm_100): two adjacent output channels per instruction, each lane rounded exactly as fmaf
+        float2 acc2[4][8];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[q][j] = bs[cg + j];
+            for (int j = 0; j < 8; ++j) acc2[q][j] = make_float2(bs[cg + 2 * j], bs[cg + 2 * j + 1]);
 #pragma unroll
         for (int tap = 0; tap < KS * KS; ++tap) {
             const int dy = tap / KS, dx = tap % KS;
 #pragma unroll
             for (int ci = 0; ci < CIN; ++ci) {
                 const float4* w4 = reinterpret_cast<const float4*>(ws + (tap * CIN + ci) * cpad + cg);
+                float2 x2[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { const float xv = in[(q >> 1) + dy][(q & 1) + dx][ci]; x2[q] = make_float2(xv, xv); }
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
                     const float4 w = w4[j4];
+                    const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const float xv = in[(q >> 1) + dy][(q & 1) + dx][ci];
-                        acc[q][j4 * 4 + 0] = fmaf(xv, w.x, acc[q][j4 * 4 + 0]);
-                        acc[q][j4 * 4 + 1] = fmaf(xv, w.y, acc[q][j4 * 4 + 1]);
-                        acc[q][j4 * 4 + 2] = fmaf(xv, w.z, acc[q][j4 * 4 + 2]);
-                        acc[q][j4 * 4 + 3] = fmaf(xv, w.w, acc[q][j4 * 4 + 3]);
+                        acc2[q][j4 * 2 + 0] = __ffma2_rn(x2[q], w01, acc2[q][j4 * 2 + 0]);
+                        acc2[q][j4 * 2 + 1] = __ffma2_rn(x2[q], w23, acc2[q][j4 * 2 + 1]);
                     }
                 }
             }
         }
+        float acc[4][16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc[q][2 * j] = acc2[q][j].x; acc[q][2 * j + 1] = acc2[q][j].y; }
         // ReLU / leaky-ReLU (slope > 0) are non-decreasing, so max-pool first and activate the survivor only:
         // max(act(a), act(b)) == act(max(a, b)) bit for bit, at a quarter of the activation work
         const int nq = p.pool ? 1 : 4;

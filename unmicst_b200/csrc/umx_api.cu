@@ -830,6 +830,24 @@ int lower_plan(umx_handle* h) {
             break;
         }
     }
+    // can the tile gather be folded into the first layer?  Only if nothing else reads the gathered input buffer.
+    {
+        const float* in = h->bufs[h->in_buf].d;
+        int readers = 0, first_reader = -1;
+        for (size_t i = 0; i < h->ops.size(); ++i) {
+            const Op& op = h->ops[i];
+            if (op.fused_away) continue;
+            bool reads = false;
+            if (op.kind == OP_CONV && op.use_first) reads = op.fp.src == in;
+            else if (op.kind == OP_CONV && op.use_tc) reads = op.tcp.skip_src == in;
+            else if (op.kind == OP_CONV) { for (int t = 0; t < op.cp.nterms; ++t) reads |= op.cp.term[t].src0 == in || op.cp.term[t].src1 == in; }
+            else if (op.kind == OP_TAPS) reads = op.taps.src == in;
+            else reads = op.tp.src == in;
+            if (reads) { ++readers; if (first_reader < 0) first_reader = (int)i; }
+        }
+        const char* e = getenv("UMX_FUSE_GATHER");
+        h->fuse_gather = (e ? atoi(e) : 1) && readers == 1 && first_reader >= 0 && h->ops[first_reader].kind == OP_CONV && h->ops[first_reader].use_first;
+    }
     return UMX_OK;
 }
 
@@ -873,7 +891,7 @@ void drain_profile(umx_handle* h) {
 }
 
 // Run the network on nb tiles already sitting in the input buffer; probs -> `probs_out` (device).
-int run_network(umx_handle* h, int nb, float* probs_out) {
+int run_network(umx_handle* h, int nb, float* probs_out, const FirstImage* fused_input = nullptr) {
     for (auto& op : h->ops) {
         if (op.fused_away) continue;
         ScopedTimer tm(h, op.prof_slot, op.flops_per_tile * nb, op.bytes_per_tile * nb + op.weight_bytes);
@@ -899,6 +917,7 @@ int run_network(umx_handle* h, int nb, float* probs_out) {
         } else if (op.kind == OP_CONV && op.use_first) {
             FirstParams fp = op.fp;
             fp.n_tiles = nb;
+            if (fused_input && fp.src == h->bufs[h->in_buf].d) fp.im = *fused_input;       // the tile gather happens inside the kernel
             UMX_CUDA_TRY(launch_first_conv(fp, h->stream));
         } else if (op.kind == OP_CONV) {
             ConvParams cp = op.cp;
@@ -1428,6 +1447,15 @@ int umx_infer_image(umx_handle* h, const void* img, int32_t dtype, int32_t n_pla
         for (int t0 = tile_begin; t0 < tile_end; t0 += h->max_batch) {
             const int nb = std::min(h->max_batch, tile_end - t0);
             gp.tile0 = t0; gp.n_tiles = nb; gp.out = h->bufs[h->in_buf].d;
+            if (h->fuse_gather && gp.lut) {
+                // integer samples at native size and nothing but the first layer reads the tiles: no gathered tile buffer
+                // at all, the first-layer kernel looks the samples up itself
+                FirstImage fi{};
+                fi.img = gp.img; fi.lut = gp.lut; fi.plane_stride = gp.plane_stride; fi.dtype = gp.dtype; fi.n_planes = gp.n_planes;
+                fi.img_row0 = gp.img_row0; fi.H = gp.H; fi.W = gp.W; fi.margin = gp.margin; fi.sub = gp.sub; fi.npc = gp.npc; fi.tile0 = t0;
+                UMX_TRY(run_network(h, nb, group_base + (size_t)(t0 - tile_begin) * S * S * K, &fi));
+                continue;
+            }
             {
                 ScopedTimer tm(h, s_gather, 0, (double)nb * S * S * (h->C * 4.0 + esz));
                 UMX_CUDA_TRY(launch_gather_tiles(gp, h->stream));

@@ -118,6 +118,7 @@ struct umx_handle {
     int num_sms = 148;
     int precision = UMX_PREC_SPLIT3;
     uint64_t single_mask = 0;                    // UMX_PREC_MIXED: ops (by index) that run with one MMA per product
+    bool fuse_gather = false;                    // the first layer is the only reader of the gathered tiles: it can read the image itself
     bool full_split = false;                     // every tensor-path op carries both planes of everything (umx_set_op_terms allowed)
     std::vector<int8_t> op_terms;                // umx_create_ex: per op, t0 | t1 << 2 (-1: what the precision implies)
     std::vector<int> chan;                       // nOutX

@@ -52,8 +52,20 @@ struct ConvParams {
 
 // First layer of the v2 graphs: 3x3 SAME conv from 1 or 2 input channels + bias + activation +
 // 2x2 max-pool, straight from the normalised tile to the pooled fp16/fp32 feature map.
+// Tile gather fused into the first layer: when lut != nullptr the kernel reads the 8/16-bit samples of the
+// image itself through the normalisation look-up table (GatherParams.lut) instead of a gathered fp32 tile buffer.
+struct FirstImage {
+    const void* img;            // [C][img_rows][W] samples (device)
+    const float* lut;           // [ch * 65537 + code]; entry n_codes = the zero padding outside the image
+    int64_t plane_stride;
+    int32_t dtype, n_planes;    // UMX_U8 / UMX_U16
+    int32_t img_row0, H, W;
+    int32_t margin, sub, npc, tile0;
+};
+
 struct FirstParams {
-    const float* src;           // [n][S][S][cin]
+    FirstImage im;
+    const float* src;           // [n][S][S][cin]   (unused when im.lut is set)
     const float* w;             // [9][cin][cout] fp32 (BN scale folded)
     const float* bias;          // [cout]
     int32_t n_tiles, S, cin, cout;
