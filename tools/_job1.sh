@@ -1,9 +1,9 @@
-mkdir -p gpurun_out/r2
-timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-timeout 600 python bench.py --steps 3 --warmup 2 --configs none --cpu-budget 0 > gpurun_out/r2/bench_g.json 2> gpurun_out/r2/bench_g.err; echo "rc=$?"; tail -2 gpurun_out/r2/bench_g.err
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r2/bench_g.json').read().strip().splitlines()[-1])
-print('mixed', round(d['value'],1), round(d['ms_per_step'],1), 'e2e', round(d['e2e']['value'],1), {k:round(v['value'],1) for k,v in d['modes'].items()}, d['parity']['max_abs_dp'], d['stitched_u8']['max_abs_u8_diff'], d['stitched_u8_whole_slide']['max_abs_u8_diff'])
-print('   '+' '.join('%s %.1f'%(k['name'].split('.conv')[0]+k['name'][-5:],k['ms']) for k in d['roofline']['kernels']))
-PY
+mkdir -p gpurun_out/r2/san2
+CS=/usr/local/cuda/bin/compute-sanitizer
+for tool in memcheck racecheck synccheck; do
+  for cfg in "mixed 1" "split3 0" "single 1"; do
+    set -- $cfg
+    UMX_TC_PAIR=$2 timeout 1200 $CS --tool $tool --error-exitcode 9 --print-limit 5 python tools/sanitize.py $1 > gpurun_out/r2/san2/${tool}_$1_pair$2.log 2>&1
+    echo "$tool $1 pair=$2 rc=$? ok=$(grep -c '\]: ok' gpurun_out/r2/san2/${tool}_$1_pair$2.log) $(grep 'ERROR SUMMARY\|RACECHECK SUMMARY' gpurun_out/r2/san2/${tool}_$1_pair$2.log | tail -1) lines=$(grep -o 'kernels_tc.cu:[0-9]*' gpurun_out/r2/san2/${tool}_$1_pair$2.log | sort | uniq -c | tr '\n' ' ')"
+  done
+done
