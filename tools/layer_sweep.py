@@ -9,15 +9,15 @@ rows = {}
 for c in cfgs:
     env = dict(os.environ, **c)
     r = subprocess.run([sys.executable, "bench.py", "--size", "4096", "--steps", "2", "--warmup", "1", "--cpu-budget", "0",
-                        "--precision", prec], capture_output=True, text=True, env=env)
-    key = " ".join(f"{k.replace('UMX_TC_', '')}={v}" for k, v in c.items())
+                        "--configs", "none", "--no-modes", "--no-crop-check", "--precision", prec], capture_output=True, text=True, env=env)
+    key = " ".join(f"{k.replace('UMX_TC_', '').replace('UMX_', '')}={v}" for k, v in c.items())
     try:
         d = json.loads(r.stdout.strip().splitlines()[-1])
     except Exception:
         print(key, "FAILED", r.stderr[-500:]); continue
     rows[key] = {k["name"]: k["ms"] for k in d["roofline"]["kernels"] if k["launches"]}
     rows[key]["MP/s"] = round(d["value"], 1)
-    rows[key]["max|dp|"] = "%.1e" % d["parity"]["max_abs_dp_vs_fp32_path"]
+    rows[key]["max|dp|"] = "%.1e" % d["parity"].get("max_abs_dp", float("nan"))
 names = list(next(iter(rows.values())).keys())
 print("%-16s" % "layer (ms)" + "".join("%18s" % k for k in rows))
 for n in names:

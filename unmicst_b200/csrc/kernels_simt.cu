@@ -10,6 +10,7 @@
 //  stitch_kernel      PI2D.patchOutput/getValidOutput as an atomic-free gather
 //                     (PartitionOfImage.py:92-122) + np.uint8(255*p) (UnMicst1-5.py:848)
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -245,165 +246,234 @@ __global__ void __launch_bounds__(NTHR) conv_simt_kernel(const __grid_constant__
 }
 
 // First layer: k x k SAME conv from 1 or 2 input channels (+ bias, activation, optional 2x2 max-pool).
-// Block: one 32x32-pixel region of one tile; thread: one 2x2 pixel block, all output channels in groups of 16.
-// Weights are read from shared memory as warp-wide broadcasts (padded to a multiple of 16 channels with zeros).
-template <int CIN, int KS>
+// Block: p.rpb consecutive 32x32-pixel regions (of one tile when rpb divides the regions per tile); thread: one 2x2 pixel
+// block, all output channels in groups of 16.  Weights are read from shared memory as warp-wide broadcasts (padded to a
+// multiple of 16 channels with zeros) and staged once per block.  The input patch is double buffered: the samples of
+// the next region are requested before the FMAs of the current one, looked up (fused gather) after its first channel
+// group and stored at its end, so the two dependent global-load latencies of the fused gather hide behind arithmetic.
+// FAST = the common configuration resolved at compile time (2x2 max-pool, leaky ReLU, fp16 planes out in whole 16-channel
+// groups, no fp32 copy): the per-group flag tests of the general path are a fifth of its instructions.
+template <int CIN, int KS, bool FAST>
 __global__ void __launch_bounds__(256) first_conv_kernel(const FirstParams p) {
     constexpr int R = KS / 2, PW = 32 + 2 * R, NB = 2 + 2 * R;
+    constexpr bool DUP = NB * NB * CIN <= 16;            // keep the patch as (x, x) pairs: FFMA2 operands without moves
+    const bool pool = FAST ? true : p.pool != 0;
+    const int act = FAST ? (int)ACT_LEAKY : p.act;
+    const bool wide_out = FAST ? true : ((p.out_cs & 15) == 0 && (p.out_plane_elems & 15) == 0);
+    const bool wide_taps = FAST ? true : ((p.taps_cs & 15) == 0 && (p.taps_plane_elems & 15) == 0);
+    constexpr int NL = (PW * PW + 255) / 256;            // patch pixels per thread
+    constexpr int XN = (PW * PW * CIN + 3) & ~3;
     extern __shared__ __align__(16) float smem[];
     const int cpad = (p.cout + 15) & ~15;
-    float* xin = smem;                                   // [PW][PW][CIN]
-    float* ws = smem + ((PW * PW * CIN + 3) & ~3);       // [KS*KS][CIN][cpad]
+    float* xin0 = smem;                                  // 2 x [PW][PW][CIN]
+    float* ws = smem + 2 * XN;                           // [KS*KS][CIN][cpad]
     float* bs = ws + KS * KS * CIN * cpad;               // [cpad]
     const int nb = p.S / 32;
-    const int n = blockIdx.x / (nb * nb);
-    const int rb = blockIdx.x % (nb * nb);
-    const int y0 = (rb / nb) * 32, x0 = (rb % nb) * 32;
-    if (p.im.lut) {
+    const bool fused = p.im.lut != nullptr;
+    const int n_codes = p.im.dtype == UMX_U8 ? 256 : 65536;
+
+    // stage 1 of a patch load: the raw sample (fused gather: its integer code; else the fp32 value) of each patch pixel.
+    // code -1 = outside the tile (the conv's zero padding); n_codes = inside the tile, outside the image (PI2D's frame).
+    int32_t raw[NL * CIN];
+    auto fetch = [&](int region) {
+        const int n = region / (nb * nb), rb = region % (nb * nb);
+        const int y0 = (rb / nb) * 32, x0 = (rb % nb) * 32;
         // PI2D.getPatch + (x - mean)/std straight from the image: tile t = (ti, tj) covers frame rows ti*sub .. +S, the
-        // frame is the image at offset (margin, margin) and 0 (-> lut[n_codes]) elsewhere; outside the TILE the conv pads 0
-        const int t = p.im.tile0 + n, ti = t / p.im.npc, tj = t - ti * p.im.npc;
-        const int n_codes = p.im.dtype == UMX_U8 ? 256 : 65536;
-        for (int i = threadIdx.x; i < PW * PW; i += 256) {
+        // frame is the image at offset (margin, margin) and 0 (-> lut[n_codes]) elsewhere
+        const int t = p.im.tile0 + n, ti = fused ? t / p.im.npc : 0, tj = fused ? t - ti * p.im.npc : 0;
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            const int i = threadIdx.x + l * 256;
             const int r = i / PW, c = i % PW;
             const int gy = y0 + r - R, gx = x0 + c - R;
-            const bool inb = gy >= 0 && gy < p.S && gx >= 0 && gx < p.S;
-            const int ir = ti * p.im.sub + gy - p.im.margin, ic = tj * p.im.sub + gx - p.im.margin;
-            const bool inside = inb && ir >= 0 && ir < p.im.H && ic >= 0 && ic < p.im.W;
+            const bool inb = i < PW * PW && gy >= 0 && gy < p.S && gx >= 0 && gx < p.S;
+            if (fused) {
+                const int ir = ti * p.im.sub + gy - p.im.margin, ic = tj * p.im.sub + gx - p.im.margin;
+                const bool inside = inb && ir >= 0 && ir < p.im.H && ic >= 0 && ic < p.im.W;
 #pragma unroll
-            for (int ci = 0; ci < CIN; ++ci) {
-                int code = n_codes;
-                if (inside) {
-                    const int64_t idx = (int64_t)(p.im.n_planes == 1 ? 0 : ci) * p.im.plane_stride + (int64_t)(ir - p.im.img_row0) * p.im.W + ic;
-                    code = p.im.dtype == UMX_U8 ? (int)__ldg(reinterpret_cast<const uint8_t*>(p.im.img) + idx)
-                                                : (int)__ldg(reinterpret_cast<const uint16_t*>(p.im.img) + idx);
+                for (int ci = 0; ci < CIN; ++ci) {
+                    int code = inb ? n_codes : -1;
+                    if (inside) {
+                        const int64_t idx = (int64_t)(p.im.n_planes == 1 ? 0 : ci) * p.im.plane_stride + (int64_t)(ir - p.im.img_row0) * p.im.W + ic;
+                        code = p.im.dtype == UMX_U8 ? (int)__ldg(reinterpret_cast<const uint8_t*>(p.im.img) + idx)
+                                                    : (int)__ldg(reinterpret_cast<const uint16_t*>(p.im.img) + idx);
+                    }
+                    raw[l * CIN + ci] = code;
                 }
-                xin[i * CIN + ci] = inb ? __ldg(p.im.lut + ci * 65537 + code) : 0.f;
+            } else {
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci)
+                    raw[l * CIN + ci] = inb ? __float_as_int(__ldg(p.src + (((int64_t)n * p.S + gy) * p.S + gx) * CIN + ci)) : 0;
             }
         }
-    } else
-    for (int i = threadIdx.x; i < PW * PW; i += 256) {
-        const int r = i / PW, c = i % PW;
-        const int gy = y0 + r - R, gx = x0 + c - R;
-        const bool inb = gy >= 0 && gy < p.S && gx >= 0 && gx < p.S;
+    };
+    // stage 2: code -> normalised fp32 through the look-up table (in place)
+    auto lookup = [&]() {
+        if (!fused) return;
 #pragma unroll
-        for (int ci = 0; ci < CIN; ++ci)
-            xin[i * CIN + ci] = inb ? __ldg(p.src + (((int64_t)n * p.S + gy) * p.S + gx) * CIN + ci) : 0.f;
-    }
+        for (int l = 0; l < NL; ++l)
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) {
+                const int code = raw[l * CIN + ci];
+                raw[l * CIN + ci] = code >= 0 ? __float_as_int(__ldg(p.im.lut + ci * 65537 + code)) : 0;
+            }
+    };
+    auto stash = [&](float* xin) {
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            const int i = threadIdx.x + l * 256;
+            if (i < PW * PW) {
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci) xin[i * CIN + ci] = __int_as_float(raw[l * CIN + ci]);
+            }
+        }
+    };
+
+    const int region0 = blockIdx.x * p.rpb;
+    fetch(region0);
     for (int i = threadIdx.x; i < KS * KS * CIN * cpad; i += 256) {
         const int c = i % cpad;
         ws[i] = c < p.cout ? __ldg(p.w + (size_t)(i / cpad) * p.cout + c) : 0.f;
     }
     for (int i = threadIdx.x; i < cpad; i += 256) bs[i] = (p.bias && i < p.cout) ? __ldg(p.bias + i) : 0.f;
+    lookup();
+    stash(xin0);
     __syncthreads();
     const int py = threadIdx.x >> 4, px = threadIdx.x & 15;
-    float in[NB][NB][CIN];
+    const int oh = pool ? p.S / 2 : p.S;
+    for (int rr = 0; rr < p.rpb; ++rr) {
+        const int region = region0 + rr;
+        const int n = region / (nb * nb), rb = region % (nb * nb);
+        const int y0 = (rb / nb) * 32, x0 = (rb % nb) * 32;
+        const float* xin = xin0 + (rr & 1) * XN;
+        const bool more = rr + 1 < p.rpb;
+        if (more) fetch(region + 1);
+        float in[NB][NB][CIN];
 #pragma unroll
-    for (int a = 0; a < NB; ++a)
+        for (int a = 0; a < NB; ++a)
 #pragma unroll
-        for (int b = 0; b < NB; ++b)
+            for (int b = 0; b < NB; ++b)
 #pragma unroll
-            for (int ci = 0; ci < CIN; ++ci) in[a][b][ci] = xin[((2 * py + a) * PW + 2 * px + b) * CIN + ci];
-    if (p.taps_out) {
-        // tap expansion of this thread's 2x2 pixels for the tensor-path consumer (lu0.conv2): channel = tap*CIN + c
-        constexpr int NCH = KS * KS * CIN;
+                for (int ci = 0; ci < CIN; ++ci) in[a][b][ci] = xin[((2 * py + a) * PW + 2 * px + b) * CIN + ci];
+        float2 in2[DUP ? NB : 1][DUP ? NB : 1][DUP ? CIN : 1];
+        if (DUP) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int64_t pix = ((int64_t)n * p.S + y0 + 2 * py + (q >> 1)) * p.S + x0 + 2 * px + (q & 1);
-            __half* o = p.taps_out + pix * p.taps_cs;
+            for (int a = 0; a < NB; ++a)
 #pragma unroll
-            const bool wide = (p.taps_cs & 15) == 0 && (p.taps_plane_elems & 15) == 0;
+                for (int b = 0; b < NB; ++b)
 #pragma unroll
-            for (int g = 0; g < (NCH + 15) / 16; ++g) {
-                float v[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int ch = g * 16 + j;
-                    v[j] = ch < NCH ? in[(q >> 1) + (ch / CIN) / KS][(q & 1) + (ch / CIN) % KS][ch % CIN] : 0.f;
-                }
-                if (wide) store_h16(o + g * 16, p.taps_plane_elems, p.taps_planes, v);
-                else {
-#pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4)
-                        if (g * 16 + j4 * 4 < p.taps_cs) store_h2x4(o + g * 16 + j4 * 4, p.taps_plane_elems, p.taps_planes, v + j4 * 4);
-                }
-            }
+                    for (int ci = 0; ci < CIN; ++ci) in2[DUP ? a : 0][DUP ? b : 0][DUP ? ci : 0] = make_float2(in[a][b][ci], in[a][b][ci]);
         }
-    }
-    const int oh = p.pool ? p.S / 2 : p.S;
-    for (int cg = 0; cg < cpad; cg += 16) {
-        // packed fp32 FMAs (FFMA2, sm_100): two adjacent output channels per instruction, each lane rounded exactly as fmaf
-        float2 acc2[4][8];
+        if (p.taps_out) {
+            // tap expansion of this thread's 2x2 pixels for the tensor-path consumer (lu0.conv2): channel = tap*CIN + c
+            constexpr int NCH = KS * KS * CIN;
+            const bool wide = wide_taps;
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < 4; ++q) {
+                const int64_t pix = ((int64_t)n * p.S + y0 + 2 * py + (q >> 1)) * p.S + x0 + 2 * px + (q & 1);
+                __half* o = p.taps_out + pix * p.taps_cs;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc2[q][j] = make_float2(bs[cg + 2 * j], bs[cg + 2 * j + 1]);
+                for (int g = 0; g < (NCH + 15) / 16; ++g) {
+                    float v[16];
 #pragma unroll
-        for (int tap = 0; tap < KS * KS; ++tap) {
-            const int dy = tap / KS, dx = tap % KS;
+                    for (int j = 0; j < 16; ++j) {
+                        const int ch = g * 16 + j;
+                        v[j] = ch < NCH ? in[(q >> 1) + (ch / CIN) / KS][(q & 1) + (ch / CIN) % KS][ch % CIN] : 0.f;
+                    }
+                    if (wide) store_h16(o + g * 16, p.taps_plane_elems, p.taps_planes, v);
+                    else {
 #pragma unroll
-            for (int ci = 0; ci < CIN; ++ci) {
-                const float4* w4 = reinterpret_cast<const float4*>(ws + (tap * CIN + ci) * cpad + cg);
-                float2 x2[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) { const float xv = in[(q >> 1) + dy][(q & 1) + dx][ci]; x2[q] = make_float2(xv, xv); }
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                    const float4 w = w4[j4];
-                    const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        acc2[q][j4 * 2 + 0] = __ffma2_rn(x2[q], w01, acc2[q][j4 * 2 + 0]);
-                        acc2[q][j4 * 2 + 1] = __ffma2_rn(x2[q], w23, acc2[q][j4 * 2 + 1]);
+                        for (int j4 = 0; j4 < 4; ++j4)
+                            if (g * 16 + j4 * 4 < p.taps_cs) store_h2x4(o + g * 16 + j4 * 4, p.taps_plane_elems, p.taps_planes, v + j4 * 4);
                     }
                 }
             }
         }
-        float acc[4][16];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { acc[q][2 * j] = acc2[q][j].x; acc[q][2 * j + 1] = acc2[q][j].y; }
-        // ReLU / leaky-ReLU (slope > 0) are non-decreasing, so max-pool first and activate the survivor only:
-        // max(act(a), act(b)) == act(max(a, b)) bit for bit, at a quarter of the activation work
-        const int nq = p.pool ? 1 : 4;
-        if (p.pool) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[0][j] = apply_act(fmaxf(fmaxf(acc[0][j], acc[1][j]), fmaxf(acc[2][j], acc[3][j])), p.act, p.leaky);
-        } else {
+        for (int cg = 0; cg < cpad; cg += 16) {
+            // packed fp32 FMAs (FFMA2, sm_100): two adjacent output channels per instruction, each lane rounded exactly as fmaf
+            float2 acc2[4][8];
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[q][j] = apply_act(acc[q][j], p.act, p.leaky);
-        }
-        for (int q = 0; q < nq; ++q) {
-            const int oy = p.pool ? (y0 / 2 + py) : (y0 + 2 * py + (q >> 1));
-            const int ox = p.pool ? (x0 / 2 + px) : (x0 + 2 * px + (q & 1));
-            const int64_t opix = ((int64_t)n * oh + oy) * oh + ox;
-            float v[16];
+                for (int j = 0; j < 8; ++j) acc2[q][j] = make_float2(bs[cg + 2 * j], bs[cg + 2 * j + 1]);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = q == 0 ? acc[0][j] : (q == 1 ? acc[1][j] : (q == 2 ? acc[2][j] : acc[3][j]));
-            if (p.out) {
-                float* o = p.out + opix * p.cout + cg;
-                if (cg + 16 <= p.cout && !(p.cout & 3)) {
+            for (int tap = 0; tap < KS * KS; ++tap) {
+                const int dy = tap / KS, dx = tap % KS;
 #pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4)
-                        reinterpret_cast<float4*>(o)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-                } else {
+                for (int ci = 0; ci < CIN; ++ci) {
+                    const float4* w4 = reinterpret_cast<const float4*>(ws + (tap * CIN + ci) * cpad + cg);
+                    float2 x2[4];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) if (cg + j < p.cout) o[j] = v[j];
+                    for (int q = 0; q < 4; ++q) {
+                        if (DUP) x2[q] = in2[DUP ? (q >> 1) + dy : 0][DUP ? (q & 1) + dx : 0][DUP ? ci : 0];
+                        else { const float xv = in[(q >> 1) + dy][(q & 1) + dx][ci]; x2[q] = make_float2(xv, xv); }
+                    }
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 w = w4[j4];
+                        const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            acc2[q][j4 * 2 + 0] = __ffma2_rn(x2[q], w01, acc2[q][j4 * 2 + 0]);
+                            acc2[q][j4 * 2 + 1] = __ffma2_rn(x2[q], w23, acc2[q][j4 * 2 + 1]);
+                        }
+                    }
                 }
             }
-            if (p.out_h) {
-                if ((p.out_cs & 15) == 0 && (p.out_plane_elems & 15) == 0 && cg + 16 <= p.out_cs)
-                    store_h16(p.out_h + opix * p.out_cs + cg, p.out_plane_elems, p.out_planes, v);
-                else {
+            if (cg == 0 && more) lookup();          // the next region's samples have arrived by now
+            float acc[4][16];
 #pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4)
-                        if (cg + j4 * 4 < p.out_cs) store_h2x4(p.out_h + opix * p.out_cs + cg + j4 * 4, p.out_plane_elems, p.out_planes, v + j4 * 4);
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { acc[q][2 * j] = acc2[q][j].x; acc[q][2 * j + 1] = acc2[q][j].y; }
+            // ReLU / leaky-ReLU (slope > 0) are non-decreasing, so max-pool first and activate the survivor only:
+            // max(act(a), act(b)) == act(max(a, b)) bit for bit, at a quarter of the activation work
+            const int nq = pool ? 1 : 4;
+            if (pool) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[0][j] = apply_act(fmaxf(fmaxf(acc[0][j], acc[1][j]), fmaxf(acc[2][j], acc[3][j])), act, p.leaky);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[q][j] = apply_act(acc[q][j], act, p.leaky);
+            }
+            if (FAST) {
+                const int64_t opix = ((int64_t)n * oh + y0 / 2 + py) * oh + x0 / 2 + px;
+                store_h16(p.out_h + opix * p.out_cs + cg, p.out_plane_elems, p.out_planes, acc[0]);
+                continue;
+            }
+            for (int q = 0; q < nq; ++q) {
+                const int oy = pool ? (y0 / 2 + py) : (y0 + 2 * py + (q >> 1));
+                const int ox = pool ? (x0 / 2 + px) : (x0 + 2 * px + (q & 1));
+                const int64_t opix = ((int64_t)n * oh + oy) * oh + ox;
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = q == 0 ? acc[0][j] : (q == 1 ? acc[1][j] : (q == 2 ? acc[2][j] : acc[3][j]));
+                if (p.out) {
+                    float* o = p.out + opix * p.cout + cg;
+                    if (cg + 16 <= p.cout && !(p.cout & 3)) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4)
+                            reinterpret_cast<float4*>(o)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) if (cg + j < p.cout) o[j] = v[j];
+                    }
+                }
+                if (p.out_h) {
+                    if (wide_out && cg + 16 <= p.out_cs)
+                        store_h16(p.out_h + opix * p.out_cs + cg, p.out_plane_elems, p.out_planes, v);
+                    else {
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4)
+                            if (cg + j4 * 4 < p.out_cs) store_h2x4(p.out_h + opix * p.out_cs + cg + j4 * 4, p.out_plane_elems, p.out_planes, v + j4 * 4);
+                    }
                 }
             }
         }
+        if (more) stash(xin0 + ((rr + 1) & 1) * XN);
+        __syncthreads();
     }
 }
 
@@ -764,23 +834,39 @@ cudaError_t launch_top_softmax(const TopParams& p, cudaStream_t s) {
 
 size_t first_conv_smem_bytes(int cin, int ks, int cout) {
     const int pw = 32 + 2 * (ks / 2), cpad = (cout + 15) & ~15;
-    return (((size_t)pw * pw * cin + 3) & ~(size_t)3) * 4 + ((size_t)ks * ks * cin * cpad + cpad) * 4;
+    return 2 * (((size_t)pw * pw * cin + 3) & ~(size_t)3) * 4 + ((size_t)ks * ks * cin * cpad + cpad) * 4;
+}
+
+template <int CIN, int KS, bool FAST>
+static cudaError_t launch_first_v(const FirstParams& p, unsigned grid, size_t sm, cudaStream_t s) {
+    if (sm > 48 * 1024) {       // per device and per call: handles on different GPUs share this process
+        cudaError_t e = cudaFuncSetAttribute(first_conv_kernel<CIN, KS, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e != cudaSuccess) return e;
+    }
+    first_conv_kernel<CIN, KS, FAST><<<grid, 256, sm, s>>>(p);
+    return cudaGetLastError();
 }
 
 template <int CIN, int KS>
 static cudaError_t launch_first(const FirstParams& p, unsigned grid, size_t sm, cudaStream_t s) {
-    if (sm > 48 * 1024) {       // per device and per call: handles on different GPUs share this process
-        cudaError_t e = cudaFuncSetAttribute(first_conv_kernel<CIN, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        if (e != cudaSuccess) return e;
-    }
-    first_conv_kernel<CIN, KS><<<grid, 256, sm, s>>>(p);
-    return cudaGetLastError();
+    static const bool no_fast = getenv("UMX_FC_FAST") && atoi(getenv("UMX_FC_FAST")) == 0;
+    const int cpad = (p.cout + 15) & ~15;
+    const bool fast = !no_fast && p.pool && p.act == ACT_LEAKY && !p.out && p.out_h && (p.out_cs & 15) == 0 &&
+                      (p.out_plane_elems & 15) == 0 && p.out_cs >= cpad &&
+                      (!p.taps_out || ((p.taps_cs & 15) == 0 && (p.taps_plane_elems & 15) == 0));
+    return fast ? launch_first_v<CIN, KS, true>(p, grid, sm, s) : launch_first_v<CIN, KS, false>(p, grid, sm, s);
 }
 
-cudaError_t launch_first_conv(const FirstParams& p, cudaStream_t s) {
-    if (p.n_tiles == 0) return cudaSuccess;
+cudaError_t launch_first_conv(const FirstParams& p_in, cudaStream_t s) {
+    if (p_in.n_tiles == 0) return cudaSuccess;
+    FirstParams p = p_in;
     const int nb = p.S / 32;
-    const unsigned grid = (unsigned)p.n_tiles * nb * nb;
+    // four regions per block (weights staged once, patch loads pipelined) when that still leaves a few waves of blocks
+    static const int force_rpb = getenv("UMX_FC_RPB") ? atoi(getenv("UMX_FC_RPB")) : 0;
+    const int64_t regions = (int64_t)p.n_tiles * nb * nb;
+    p.rpb = (regions % 4 == 0 && regions / 4 >= 4 * 148 * 2) ? 4 : 1;
+    if (force_rpb > 0 && regions % force_rpb == 0) p.rpb = force_rpb;
+    const unsigned grid = (unsigned)(regions / p.rpb);
     const size_t sm = first_conv_smem_bytes(p.cin, p.ks, p.cout);
     if (p.cin == 1 && p.ks == 3) return launch_first<1, 3>(p, grid, sm, s);
     if (p.cin == 2 && p.ks == 3) return launch_first<2, 3>(p, grid, sm, s);

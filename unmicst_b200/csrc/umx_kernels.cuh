@@ -81,6 +81,7 @@ struct FirstParams {
     __half* taps_out;           // fp16 hi[/lo] planes [planes][n][S][S][taps_cs] or nullptr
     int64_t taps_plane_elems;
     int32_t taps_planes, taps_cs;
+    int32_t rpb;                // 32x32 regions per block (set by the launcher)
 };
 
 struct TapsParams {             // k x k tap expansion (im2col of the SAME-padded tile) of a 1-2 channel fp32 buffer
