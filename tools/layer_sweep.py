@@ -5,10 +5,11 @@ prec = sys.argv[1] if len(sys.argv) > 1 else "single"
 axes = [a.split("=") for a in sys.argv[2:]] or [["UMX_TC_PAIR", "0,1"], ["UMX_TC_STAGES", "2,3,4,8"]]
 keys = [a[0] for a in axes]
 cfgs = [dict(zip(keys, vals)) for vals in itertools.product(*[a[1].split(",") for a in axes])]
+extra = os.environ.get("SWEEP_ARGS", "--size 4096").split()       # e.g. SWEEP_ARGS="--workload cyto2tma --size 6144"
 rows = {}
 for c in cfgs:
     env = dict(os.environ, **c)
-    r = subprocess.run([sys.executable, "bench.py", "--size", "4096", "--steps", "2", "--warmup", "1", "--cpu-budget", "0",
+    r = subprocess.run([sys.executable, "bench.py", *extra, "--steps", "2", "--warmup", "1", "--cpu-budget", "0",
                         "--configs", "none", "--no-modes", "--no-crop-check", "--precision", prec], capture_output=True, text=True, env=env)
     key = " ".join(f"{k.replace('UMX_TC_', '').replace('UMX_', '')}={v}" for k, v in c.items())
     try:

@@ -621,7 +621,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                                 } else {
                                     if (PAIR) tma_load_4d_pair(db, &mapB, fullB0, kc, ncol, 0, 0);
                                     else tma_load_4d(db, &mapB, fullB0, kc, ncol, 0, 0);
-                                    db += gb * b_plane_bytes;                      // resident main slabs hold the hi plane only
+                                    db += p.res_m_planes * gb * b_plane_bytes;     // [plane][tap][rows]: hi, + lo when a full-slab source uses a_hi*w_lo
                                 }
                             }
                         }
@@ -739,7 +739,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             if (resident) {
                                 // weights stay put: slab cb's taps start at cb * gb tiles, addressed by their device tap index
                                 // (a centre-only slab keeps just that one tap, so the slabs after it start gb - 1 tiles earlier)
-                                const uint32_t r_off = (uint32_t)((centre_only ? nch0 * gb + (cb - nch0) * p.res_c_planes : cb * gb) * b_plane_bytes);
+                                const uint32_t r_off = (uint32_t)((centre_only ? nch0 * gb * p.res_m_planes + (cb - nch0) * p.res_c_planes : cb * gb * p.res_m_planes) * b_plane_bytes);
                                 const uint32_t b_lo = desc_lo(smem_u32(smem_b) + r_off) + (centre_only ? 0u : (sub ? wi1 : wi0));
                                 if (exp_mma & 128) {}
                                 else halo_taps_terms<PAIR>(tsel, nk, te, tmem_ds, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, centre_only ? b16 : bp16, b16, sx, rb, nx, ix, accumulate);

@@ -598,15 +598,15 @@ int lower_conv_tc(umx_handle* h, Op& op) {
             {
                 const int nc0 = (tp.c0 + 63) / 64, nc1 = (tp.c1 + 63) / 64, n_chunks = nc0 + nc1;
                 // (the slabs of a 1x1 term exist at the centre tap only: one tile each instead of ntaps_w)
-                // resident tiles hold the hi plane; the one-tile slabs of a 1x1 term may add their lo plane
                 const size_t tile = (size_t)(tp.pair ? tp.n_t / 2 : tp.n_t) * 128;
-                const bool main_hi_only = (tp.terms0 & 1) == 0 && (tp.a1_center || (tp.terms1 & 1) == 0);
+                // full slabs keep the lo plane too when some full-slab source issues the a_hi*w_lo term (narrow layers: it still fits)
+                tp.res_m_planes = ((tp.terms0 & 1) || (!tp.a1_center && nc1 > 0 && (tp.terms1 & 1))) ? 2 : 1;
                 tp.res_c_planes = (tp.a1_center && (tp.terms1 & 1)) ? 2 : 1;
-                const size_t res = ((size_t)nc0 * ntaps_w + (size_t)nc1 * (tp.a1_center ? tp.res_c_planes : ntaps_w)) * tile;
+                const size_t res = ((size_t)nc0 * ntaps_w * tp.res_m_planes + (size_t)nc1 * (tp.a1_center ? tp.res_c_planes : ntaps_w * tp.res_m_planes)) * tile;
                 const char* e = getenv("UMX_TC_RESIDENT");
-                // (weights hi plane only for every full slab: no a_hi*w_lo term there; with both activation planes in a patch
-                // slot two slots are accepted - in this mode nothing but patches moves, so no patch waits behind a weight load)
-                if ((e ? atoi(e) : 1) && tp.n_ntiles == 1 && ntaps_w <= 9 && main_hi_only && budget >= res + (tp.planes_a == 2 ? 2 : 3) * ab) {
+                // (with both activation planes in a patch slot two slots are accepted - in this mode nothing but patches
+                // moves, so no patch waits behind a weight load)
+                if ((e ? atoi(e) : 1) && tp.n_ntiles == 1 && ntaps_w <= 9 && tp.res_m_planes <= tp.planes_b && budget >= res + (tp.planes_a == 2 ? 2 : 3) * ab) {
                     tp.b_resident = 1; tp.gb = ntaps_w; tp.b_stages = n_chunks; tp.b_res_bytes = (int32_t)res;
                     tp.stages = (int)std::min<size_t>(6, (budget - res) / ab);
                 }
@@ -614,7 +614,7 @@ int lower_conv_tc(umx_handle* h, Op& op) {
             // the producer runs the patch loads stages-1 slabs ahead of the weight loads of the same slab stream; with only
             // two patch slots the patch of slab s+1 would queue behind weights that cannot all land before that very
             // patch is consumed (a weight ring shorter than a slab's taps): a deadlock, so such layers run in plain mode
-            if (tp.b_stages < 2 || (tp.stages < 3 && !tp.b_resident)) { tp.halo = 0; tp.halo_nh = 0; tp.bw = std::min(a0.w, 16); tp.bh = std::min(a0.h, 128 / tp.bw); tp.bn = 128 / (tp.bw * tp.bh); }
+            if (!tp.b_resident && (tp.b_stages < 2 || tp.stages < 3)) { tp.halo = 0; tp.halo_nh = 0; tp.bw = std::min(a0.w, 16); tp.bh = std::min(a0.h, 128 / tp.bw); tp.bn = 128 / (tp.bw * tp.bh); }
         }
         {
             const char* e = getenv("UMX_TC_MERGE_PX");
@@ -703,7 +703,7 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     UMX_CUDA_TRY(cudaMalloc(&dw, wh.size() * sizeof(__half)));
     h->dev_allocs.push_back(reinterpret_cast<float*>(dw));
     UMX_CUDA_TRY(cudaMemcpy(dw, wh.data(), wh.size() * sizeof(__half), cudaMemcpyHostToDevice));
-    int rc = make_weight_tensor_map(&op.mapB, dw, planes_b, taps_dev, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, tp.b_resident ? 1 : planes_b, box_taps);
+    int rc = make_weight_tensor_map(&op.mapB, dw, planes_b, taps_dev, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, tp.b_resident ? tp.res_m_planes : planes_b, box_taps);
     if (rc) { set_error("%s: cuTensorMapEncodeTiled(weights) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
     op.mapB1 = op.mapB;
     if (tp.halo && !tp.b_resident && planes_b == 2 && (!(tp.terms0 & 1) || (a1 && !(tp.terms1 & 1)))) {
