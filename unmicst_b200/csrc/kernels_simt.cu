@@ -63,6 +63,23 @@ __device__ __forceinline__ void store_h16(__half* o, int64_t plane_elems, int pl
     }
 }
 
+// 8 consecutive channels: one 16-byte store per plane
+__device__ __forceinline__ void store_h8(__half* o, int64_t plane_elems, int planes, const float* v) {
+    __half2 hi[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hi[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(hi);
+    if (planes == 2) {
+        __half2 lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(hi[j]);
+            lo[j] = __floats2half2_rn(v[2 * j] - f.x, v[2 * j + 1] - f.y);
+        }
+        *reinterpret_cast<uint4*>(o + plane_elems) = *reinterpret_cast<const uint4*>(lo);
+    }
+}
+
 // Each CTA: 128 output pixels (nt image tiles x ph x pw) x 64 output channels of one phase.
 // Each thread: a 2x4 pixel patch x 4 output channels (32 fp32 accumulators).
 __global__ void __launch_bounds__(NTHR) conv_simt_kernel(const __grid_constant__ ConvParams p) {
@@ -251,16 +268,16 @@ __global__ void __launch_bounds__(NTHR) conv_simt_kernel(const __grid_constant__
 // multiple of 16 channels with zeros) and staged once per block.  The input patch is double buffered: the samples of
 // the next region are requested before the FMAs of the current one, looked up (fused gather) after its first channel
 // group and stored at its end, so the two dependent global-load latencies of the fused gather hide behind arithmetic.
-// FAST = the common configuration resolved at compile time (2x2 max-pool, leaky ReLU, fp16 planes out in whole 16-channel
-// groups, no fp32 copy): the per-group flag tests of the general path are a fifth of its instructions.
+// FAST = the common configuration resolved at compile time (2x2 max-pool, leaky ReLU, fp16 planes out, no fp32 copy):
+// the per-group flag tests of the general path are a fifth of its instructions.
 template <int CIN, int KS, bool FAST>
-__global__ void __launch_bounds__(256) first_conv_kernel(const FirstParams p) {
+__global__ void __launch_bounds__(256, (KS == 3 && (FAST || CIN == 1)) ? 2 : 0) first_conv_kernel(const FirstParams p) {
     constexpr int R = KS / 2, PW = 32 + 2 * R, NB = 2 + 2 * R;
     constexpr bool DUP = NB * NB * CIN <= 16;            // keep the patch as (x, x) pairs: FFMA2 operands without moves
     const bool pool = FAST ? true : p.pool != 0;
     const int act = FAST ? (int)ACT_LEAKY : p.act;
-    const bool wide_out = FAST ? true : ((p.out_cs & 15) == 0 && (p.out_plane_elems & 15) == 0);
-    const bool wide_taps = FAST ? true : ((p.taps_cs & 15) == 0 && (p.taps_plane_elems & 15) == 0);
+    const bool wide_out = (p.out_cs & 15) == 0 && (p.out_plane_elems & 15) == 0;
+    const bool wide_taps = (p.taps_cs & 15) == 0 && (p.taps_plane_elems & 15) == 0;
     constexpr int NL = (PW * PW + 255) / 256;            // patch pixels per thread
     constexpr int XN = (PW * PW * CIN + 3) & ~3;
     extern __shared__ __align__(16) float smem[];
@@ -440,7 +457,12 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const FirstParams p) {
             }
             if (FAST) {
                 const int64_t opix = ((int64_t)n * oh + y0 / 2 + py) * oh + x0 / 2 + px;
-                store_h16(p.out_h + opix * p.out_cs + cg, p.out_plane_elems, p.out_planes, acc[0]);
+                __half* o = p.out_h + opix * p.out_cs + cg;
+                if (wide_out && cg + 16 <= p.out_cs) store_h16(o, p.out_plane_elems, p.out_planes, acc[0]);
+                else {                              // channel strides are multiples of 8: 16-byte stores
+                    if (cg < p.out_cs) store_h8(o, p.out_plane_elems, p.out_planes, acc[0]);
+                    if (cg + 8 < p.out_cs) store_h8(o + 8, p.out_plane_elems, p.out_planes, acc[0] + 8);
+                }
                 continue;
             }
             for (int q = 0; q < nq; ++q) {
@@ -850,10 +872,8 @@ static cudaError_t launch_first_v(const FirstParams& p, unsigned grid, size_t sm
 template <int CIN, int KS>
 static cudaError_t launch_first(const FirstParams& p, unsigned grid, size_t sm, cudaStream_t s) {
     static const bool no_fast = getenv("UMX_FC_FAST") && atoi(getenv("UMX_FC_FAST")) == 0;
-    const int cpad = (p.cout + 15) & ~15;
-    const bool fast = !no_fast && p.pool && p.act == ACT_LEAKY && !p.out && p.out_h && (p.out_cs & 15) == 0 &&
-                      (p.out_plane_elems & 15) == 0 && p.out_cs >= cpad &&
-                      (!p.taps_out || ((p.taps_cs & 15) == 0 && (p.taps_plane_elems & 15) == 0));
+    const bool fast = !no_fast && p.pool && p.act == ACT_LEAKY && !p.out && p.out_h && (p.out_cs & 7) == 0 &&
+                      (p.out_plane_elems & 7) == 0;
     return fast ? launch_first_v<CIN, KS, true>(p, grid, sm, s) : launch_first_v<CIN, KS, false>(p, grid, sm, s);
 }
 
