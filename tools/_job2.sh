@@ -1,14 +1,11 @@
-mkdir -p gpurun_out/r2/fc
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-for w in duo4k; do
-timeout 300 python bench.py --workload $w --steps 3 --warmup 2 --cpu-budget 0 --configs none --no-modes --no-crop-check > gpurun_out/r2/fc/bench3_$w.json 2> gpurun_out/r2/fc/bench3_$w.err
-tail -c 300 gpurun_out/r2/fc/bench3_$w.err
-done
+mkdir -p gpurun_out/r2/final
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/r2/final/bench_1gpu.json 2> gpurun_out/r2/final/bench_1gpu.err
+tail -c 400 gpurun_out/r2/final/bench_1gpu.err
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "timed_resident/" -c 400 --csv --log-file gpurun_out/r2/final/launches_4k.csv python bench.py --size 4096 --steps 2 --warmup 1 --cpu-budget 0 --configs none --no-modes --no-crop-check > gpurun_out/r2/final/ncu_bench.log 2>&1
 python - <<'PY'
 import json
-for w in ("duo4k",):
-    d=json.loads(open(f"gpurun_out/r2/fc/bench3_{w}.json").read().strip().splitlines()[-1])
-    print(w, d["value"], d["ms_per_step"], d["config"].get("precision"), d["parity"]["max_abs_dp"])
-    for k in d["roofline"]["kernels"][:3]: print("  ", k["name"], k["ms"], k["mma_x"])
-    print(d["roofline"]["step"])
+d=json.loads(open("gpurun_out/r2/final/bench_1gpu.json").read().strip().splitlines()[-1])
+print(d["value"], d["ms_per_step"], d["e2e"], d["parity"]["max_abs_dp"], d["stitched_u8"], d["modes"])
+for c in d.get("configs",[]): print(c.get("workload"), c.get("value"), (c.get("e2e") or {}).get("value"), (c.get("roofline") or {}).get("step",{}) and c["roofline"]["step"].get("frac"))
 PY
+wc -l gpurun_out/r2/final/launches_4k.csv
