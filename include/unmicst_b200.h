@@ -220,7 +220,8 @@ int64_t umx_debug_buffer(umx_handle* h, const char* name, int32_t n_tiles, float
 int64_t umx_launch_count(umx_handle* h);
 
 /* How op `op_index` was lowered (diagnostics, calibration): out[0..11] = on the tensor path, halo mode, CTA pairs, patch /
- * ring slots, weight slots, taps per weight slot, weights resident in shared memory, conv-transpose px merge, planes per
+ * ring slots, weight slots, taps per weight slot, weights resident in shared memory (2 = resident with the N-concatenated
+ * a_hi x [w_hi | w_lo] MMA), conv-transpose px merge, planes per
  * activation slot, planes per weight slot, correction terms of source 0, of source 1. */
 int umx_op_info(umx_handle* h, int32_t op_index, int32_t* out, int32_t capacity);
 

@@ -168,6 +168,32 @@ def test_per_source_correction_terms_v2():
     assert not np.array_equal(built, split) and not np.array_equal(built, single)
 
 
+def test_wide_correction_mma_of_narrow_layers(monkeypatch):
+    """Narrow weight-stationary layers (Cyto2 lu0.conv2, N = 32) multiply a_hi by [w_hi | w_lo] in one MMA of twice the
+    width and add the two accumulator halves in the epilogue (umx_op_info: resident == 2).  For every term assignment of
+    that layer - including one whose first source has no a_hi*w_lo term, where the odd CTA supplies zeros - the result
+    equals the three-MMA form up to the order of the fp32 additions."""
+    from unmicst_b200.engine import tensor_ops
+    m = modelzoo.synthetic_model("CytoplasmIncell2", seed=0)
+    rng = np.random.default_rng(5)
+    tiles = rng.normal(size=(2, 256, 256, 1)).astype(np.float32)
+    want = _oracle_fw(m)(tiles)
+    op = [i for i, n in tensor_ops(m) if n == "lu0.conv2"][0]
+    cases = [15, 3, 1 | 1 << 2, 2 | 1 << 2, 2 | 3 << 2, 0]
+    got = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("UMX_TC_NCAT", flag)
+        with _engine(m, precision="split3") as e:
+            assert e.op_info(op)["resident"] == (2 if flag == "1" else 1)
+            for t in cases:
+                e.set_op_terms(op, t)
+                got[flag, t] = e.forward_tiles(tiles)
+    for t in cases:
+        assert np.abs(got["1", t] - got["0", t]).max() < 1e-5, t
+    _check_probs(got["1", 15], want)
+    assert not np.array_equal(got["1", 0], got["1", 15])            # the terms are really switched
+
+
 def test_mixed_precision_masks_v2():
     """Any subset of layers may run with one MMA per product: all-zero mask == split3 bit for bit, a partial mask and
     the full mask stay within the contract."""

@@ -1,11 +1,12 @@
-mkdir -p gpurun_out/r2/final
-timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/r2/final/bench_1gpu.json 2> gpurun_out/r2/final/bench_1gpu.err
-tail -c 400 gpurun_out/r2/final/bench_1gpu.err
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "timed_resident/" -c 400 --csv --log-file gpurun_out/r2/final/launches_4k.csv python bench.py --size 4096 --steps 2 --warmup 1 --cpu-budget 0 --configs none --no-modes --no-crop-check > gpurun_out/r2/final/ncu_bench.log 2>&1
-python - <<'PY'
-import json
-d=json.loads(open("gpurun_out/r2/final/bench_1gpu.json").read().strip().splitlines()[-1])
-print(d["value"], d["ms_per_step"], d["e2e"], d["parity"]["max_abs_dp"], d["stitched_u8"], d["modes"])
-for c in d.get("configs",[]): print(c.get("workload"), c.get("value"), (c.get("e2e") or {}).get("value"), (c.get("roofline") or {}).get("step",{}) and c["roofline"]["step"].get("frac"))
+for rep in 1 2; do
+for lib in A B; do
+  if [ $lib = B ]; then export UNMICST_B200_LIB=$PWD/tools/_libB.so; else unset UNMICST_B200_LIB; fi
+  timeout 200 python bench.py --size 6144 --steps 3 --warmup 2 --cpu-budget 0 --configs none --no-modes --no-crop-check > /tmp/o.json 2>/tmp/o.err
+  python - "$lib" <<'PY'
+import json,sys
+d=json.loads(open("/tmp/o.json").read().strip().splitlines()[-1])
+k={x["name"]:x["ms"] for x in d["roofline"]["kernels"]}
+print(sys.argv[1], round(d["value"],1), d["config"]["precision"], {n:k[n] for n in ("ld1.conv0","lu1.conv2","lu0.convT","lu0.conv2+lt","lu1.convT")})
 PY
-wc -l gpurun_out/r2/final/launches_4k.csv
+done
+done

@@ -28,6 +28,11 @@ namespace umx {
 
 namespace {
 
+#ifdef UMX_NO_NCAT                           // A/B builds: the N-concatenated correction MMA compiled out
+constexpr bool kNcat = false;
+#else
+constexpr bool kNcat = true;
+#endif
 constexpr int kEpiWarps = 8;                 // epilogue warps: kEpiSub per TMEM lane quarter, each a share of the N columns
 constexpr int kEpiSub = kEpiWarps / 4;
 constexpr int kThreads = 64 + 32 * kEpiWarps; // warp 0 TMA, warp 1 MMA, then the epilogue warps
@@ -304,6 +309,36 @@ __device__ __forceinline__ void halo_taps_nk(int terms, int nk, int ng, uint32_t
     else if (nk == 1) halo_taps<PAIR, 1, TERMS>(terms, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
     else if (nk == 2) halo_taps<PAIR, 2, TERMS>(terms, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
     else halo_taps<PAIR, 3, TERMS>(terms, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, bp16, b16, sx, row_back, nx, ix, accumulate);
+}
+
+// N-concatenated variant (p.ncat): per product one MMA of width 2*n_t, a_hi x X = [w_hi | w_lo] (or [w_hi | 0] for a source without
+// the a_hi*w_lo term), plus a_lo x Y (w_hi, width n_t) when the source has the a_lo*w_hi term.  y16 = offset of Y behind X.
+template <bool PAIR, int NK>
+__device__ __forceinline__ void halo_taps_ncat(bool a_lo_t, int ng, uint32_t tmem_d, uint32_t& a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t idesc2, uint32_t a_plane16, uint32_t y16, uint32_t btap16, int sx, int row_back,
+                                               int nx, int& ix, uint32_t& accumulate) {
+    for (int j = 0; j < ng; ++j, b_lo += btap16) {
+        umma_issue<PAIR>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc2, accumulate);
+        accumulate = 1;
+        if (a_lo_t) umma_acc<PAIR>(tmem_d, a_lo + a_plane16, a_hi, b_lo + y16, b_hi, idesc);
+#pragma unroll
+        for (int k = 1; k < NK; ++k) {
+            umma_acc<PAIR>(tmem_d, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc2);
+            if (a_lo_t) umma_acc<PAIR>(tmem_d, a_lo + a_plane16 + 2 * k, a_hi, b_lo + y16 + 2 * k, b_hi, idesc);
+        }
+        a_lo += sx;
+        if (++ix == nx) { ix = 0; a_lo += row_back; }
+    }
+}
+template <bool PAIR>
+__device__ __forceinline__ void halo_taps_ncat_nk(int terms, int nk, int ng, uint32_t tmem_d, uint32_t& a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                  uint32_t idesc, uint32_t idesc2, uint32_t a_plane16, uint32_t y16, uint32_t btap16, int sx, int row_back,
+                                                  int nx, int& ix, uint32_t& accumulate) {
+    const bool al = (terms & 2) != 0;
+    if (nk == 4) halo_taps_ncat<PAIR, 4>(al, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, idesc2, a_plane16, y16, btap16, sx, row_back, nx, ix, accumulate);
+    else if (nk == 1) halo_taps_ncat<PAIR, 1>(al, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, idesc2, a_plane16, y16, btap16, sx, row_back, nx, ix, accumulate);
+    else if (nk == 2) halo_taps_ncat<PAIR, 2>(al, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, idesc2, a_plane16, y16, btap16, sx, row_back, nx, ix, accumulate);
+    else halo_taps_ncat<PAIR, 3>(al, ng, tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, idesc2, a_plane16, y16, btap16, sx, row_back, nx, ix, accumulate);
 }
 
 // per-slab dispatch on the correction terms of the slab's source
@@ -614,6 +649,25 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             for (int cb = 0; cb < n_chunks; ++cb) {
                                 const bool second = cb >= nch0;
                                 const int kc = (second ? c0s : 0) + (second ? cb - nch0 : cb) * 64;
+                                if (kNcat && TOPK > 0 && PAIR && p.ncat) {
+                                    // one-tile boxes.  Full slab, per tap: X = n_t rows of B for the wide MMA (even CTA: w_hi; odd CTA:
+                                    // w_lo, or zeros - rows beyond cout - for a source without the a_hi*w_lo term), then Y = this
+                                    // CTA's half of w_hi.  Centre-only slab: hi [+ lo] tile as in the plain resident layout.
+                                    if (second && a1c) {
+                                        tma_load_4d_pair(db, &mapB, fullB0, kc, ncol, ctap, 0);
+                                        if (p.res_c_planes == 2) tma_load_4d_pair(db + b_plane_bytes, &mapB, fullB0, kc, ncol, ctap, 1);
+                                        db += p.res_c_planes * b_plane_bytes;
+                                    } else {
+                                        const bool w_lo = ((second ? p.terms1 : p.terms0) & 1) != 0;
+                                        const int xrow = (rank == 0 || w_lo) ? 0 : 2 * n_t, xplane = (rank == 1 && w_lo) ? 1 : 0;
+                                        for (int t = 0; t < gb; ++t) {
+                                            tma_load_4d_pair(db, &mapB, fullB0, kc, xrow, t, xplane);
+                                            tma_load_4d_pair(db + b_plane_bytes, &mapB, fullB0, kc, xrow + n_t / 2, t, xplane);
+                                            tma_load_4d_pair(db + 2 * b_plane_bytes, &mapB, fullB0, kc, ncol, t, 0);
+                                            db += 3 * b_plane_bytes;
+                                        }
+                                    }
+                                } else
                                 if (second && a1c) {        // 1x1 term: only its centre tap exists (one-tap box)
                                     if (PAIR) tma_load_4d_pair(db, &mapB1, fullB0, kc, ncol, ctap, 0);
                                     else tma_load_4d(db, &mapB1, fullB0, kc, ncol, ctap, 0);
@@ -696,7 +750,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const int pw = p.pw, hx0 = p.hx0, hy0 = p.hy0, n_chunks = nch0 + nch1;
                 const int prow = p.halo_nh ? pw * p.bn : pw;           // pixels between two image rows inside the patch
                 const uint32_t a_hi = desc_hi((uint32_t)pw * 128u);     // consecutive 8-pixel rows are one patch row apart
-                const uint32_t b16 = b_plane16;                        // weight slot = [plane][tap][rows]: taps one plane tile apart
+                const bool ncat = kNcat && TOPK > 0 && PAIR && p.ncat != 0;      // (only the kernels with the fused lt epilogue carry this path: see lower_conv_tc)
+                const uint32_t idesc2 = (1u << 4) | ((uint32_t)(p.n_t >> 2) << 17) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);   // width 2*n_t
+                const uint32_t acc_cols = ncat ? 2u * (uint32_t)p.n_t : (uint32_t)p.n_t;      // accumulator columns of one (sub-)phase
+                const uint32_t b16 = ncat ? 3 * b_plane16 : b_plane16;  // weight slot = [plane][tap][rows]: taps one plane tile apart (ncat: [tap][X, X, Y])
                 const uint32_t bp16 = (uint32_t)gb * b_plane16;
                 int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
                 const bool resident = p.b_resident != 0;
@@ -731,7 +788,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         const bool centre_only = second && a1c;
                         for (int sub = 0; sub < nsub; ++sub) {        // the taps of one sub-phase against this slab's patch
                             const int sx = sub ? sx1 : sx0, rb = sub ? rb1 : rb0, nx = sub ? nx1 : nx0;
-                            const uint32_t tmem_ds = sub ? tmem_d + (uint32_t)p.n_t : tmem_d;
+                            const uint32_t tmem_ds = sub ? tmem_d + acc_cols : tmem_d;
                             uint32_t accumulate = sub ? accum1 : accum0;
                             const int te = centre_only ? 1 : (sub ? nt1 : nt0);
                             uint32_t a_lo = a_lo0 + (centre_only ? c_off : (sub ? off1 : off0));
@@ -742,7 +799,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                                 const uint32_t r_off = (uint32_t)((centre_only ? nch0 * gb * p.res_m_planes + (cb - nch0) * p.res_c_planes : cb * gb * p.res_m_planes) * b_plane_bytes);
                                 const uint32_t b_lo = desc_lo(smem_u32(smem_b) + r_off) + (centre_only ? 0u : (sub ? wi1 : wi0));
                                 if (exp_mma & 128) {}
-                                else halo_taps_terms<PAIR>(tsel, nk, te, tmem_ds, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, centre_only ? b16 : bp16, b16, sx, rb, nx, ix, accumulate);
+                                else if (ncat && !centre_only) halo_taps_ncat_nk<PAIR>(tsel, nk, te, tmem_ds, a_lo, a_hi, b_lo, b_hi, idesc, idesc2, a_plane16, 2 * b_plane16, b16, sx, rb, nx, ix, accumulate);
+                                else halo_taps_terms<PAIR>(tsel, nk, te, tmem_ds, a_lo, a_hi, b_lo, b_hi, idesc, a_plane16, centre_only ? b_plane16 : bp16, b16, sx, rb, nx, ix, accumulate);
                             } else
                             for (int t0 = 0; t0 < te; t0 += gb) {
                                 const int ng = min(gb, te - t0);
@@ -821,7 +879,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const bool px_split = nsub == 2;
         const int g_lo = px_split ? 0 : sub * (n8 / kEpiSub) + min(sub, n8 % kEpiSub);          // first column group (channels)
         const int g_n = px_split ? n8 : n8 / kEpiSub + (sub < n8 % kEpiSub ? 1 : 0);
-        const uint32_t col0 = (uint32_t)((px_split ? sub * n_t : 0) + g_lo * 8);                 // first TMEM column
+        const bool fold = kNcat && TOPK > 0 && PAIR && HALO && p.ncat != 0;      // the accumulator is [0, n_t) + [n_t, 2 n_t): see halo_taps_ncat
+        const uint32_t col0 = (uint32_t)((px_split ? sub * (fold ? 2 * n_t : n_t) : 0) + g_lo * 8);                 // first TMEM column
         const int px_off = px_split ? sub : 0;
         // x16 TMEM loads per warp, plus one x8 load for an odd group count; timing experiments: 8 = first chunk
         // only, 32 = barrier handshake only, 16 = no global stores
@@ -861,31 +920,50 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             // the TMEM load of the next chunk is in flight while the current one is processed; an odd first group is
             // taken alone so that every 16-column chunk starts on a 32-byte boundary of the fp16 row (256-bit stores)
             uint32_t ra[16], rb[16], rt[8];
+            uint32_t ra2[16], rb2[16], rt2[8];            // ncat: the same columns of the second accumulator half
+            auto ld16 = [&](uint32_t addr, uint32_t (&r)[16], uint32_t (&r2)[16]) { tmem_ld16_issue(addr, r); if (fold) tmem_ld16_issue(addr + (uint32_t)n_t, r2); };
+            auto ld8 = [&](uint32_t addr, uint32_t (&r)[8], uint32_t (&r2)[8]) { tmem_ld8_issue(addr, r); if (fold) tmem_ld8_issue(addr + (uint32_t)n_t, r2); };
+            auto add16 = [&](uint32_t (&r)[16], const uint32_t (&r2)[16]) {
+                if (fold) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+                }
+            };
+            auto add8 = [&](uint32_t (&r)[8], const uint32_t (&r2)[8]) {
+                if (fold) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+                }
+            };
             const uint32_t tb16 = tbase + lead8 * 8;
             const int cb16 = co0 + lead8 * 8;
             float* of16 = of + lead8 * 8; __half* oh16 = oh + lead8 * 8;
-            if (lead8) tmem_ld8_issue(tbase, rt); else if (n_full > 0) tmem_ld16_issue(tb16, ra); else if (tail8) tmem_ld8_issue(tb16, rt);
+            if (lead8) ld8(tbase, rt, rt2); else if (n_full > 0) ld16(tb16, ra, ra2); else if (tail8) ld8(tb16, rt, rt2);
             if (lead8) {
                 tmem_ld_wait();
-                if (n_full > 0) tmem_ld16_issue(tb16, ra);
+                add8(rt, rt2);
+                if (n_full > 0) ld16(tb16, ra, ra2);
                 epi_chunk<8, SKIPC, TOPK>(p, e, rt, co0, xs, writer, of, oh, z);
                 __syncwarp();        // reconverge before the next .sync.aligned TMEM instruction
-                if (n_full == 0 && tail8) tmem_ld8_issue(tb16, rt);
+                if (n_full == 0 && tail8) ld8(tb16, rt, rt2);
             }
             for (int i = 0; i < n_full; i += 2) {
                 tmem_ld_wait();
-                if (i + 1 < n_full) tmem_ld16_issue(tb16 + (i + 1) * 16, rb); else if (tail8) tmem_ld8_issue(tb16 + n_full * 16, rt);
+                add16(ra, ra2);
+                if (i + 1 < n_full) ld16(tb16 + (i + 1) * 16, rb, rb2); else if (tail8) ld8(tb16 + n_full * 16, rt, rt2);
                 epi_chunk<16, SKIPC, TOPK>(p, e, ra, cb16 + i * 16, xs, writer, of16 + i * 16, oh16 + i * 16, z);
                 __syncwarp();
                 if (i + 1 < n_full) {
                     tmem_ld_wait();
-                    if (i + 2 < n_full) tmem_ld16_issue(tb16 + (i + 2) * 16, ra); else if (tail8) tmem_ld8_issue(tb16 + n_full * 16, rt);
+                    add16(rb, rb2);
+                    if (i + 2 < n_full) ld16(tb16 + (i + 2) * 16, ra, ra2); else if (tail8) ld8(tb16 + n_full * 16, rt, rt2);
                     epi_chunk<16, SKIPC, TOPK>(p, e, rb, cb16 + (i + 1) * 16, xs, writer, of16 + (i + 1) * 16, oh16 + (i + 1) * 16, z);
                     __syncwarp();
                 }
             }
             if (tail8) {
                 tmem_ld_wait();
+                add8(rt, rt2);
                 epi_chunk<8, SKIPC, TOPK>(p, e, rt, cb16 + n_full * 16, xs, writer, of16 + n_full * 16, oh16 + n_full * 16, z);
                 __syncwarp();
             }

@@ -604,9 +604,30 @@ int lower_conv_tc(umx_handle* h, Op& op) {
                 tp.res_c_planes = (tp.a1_center && (tp.terms1 & 1)) ? 2 : 1;
                 const size_t res = ((size_t)nc0 * ntaps_w * tp.res_m_planes + (size_t)nc1 * (tp.a1_center ? tp.res_c_planes : ntaps_w * tp.res_m_planes)) * tile;
                 const char* e = getenv("UMX_TC_RESIDENT");
+                // N-concatenated correction (narrow layers, CTA pairs): one MMA of width 2*n_t multiplies a_hi by [w_hi | w_lo]
+                // (the even CTA supplies w_hi as its half of the B rows, the odd CTA w_lo) and the epilogue adds the two halves
+                // of the accumulator: a product with the a_hi*w_lo term costs one MMA less, and below N ~ 110 an MMA costs the
+                // single issuing thread the same ~55 cycles whatever its width.  Per tap a slab keeps [X: n_t rows | Y: n_t/2
+                // rows of w_hi for the a_lo*w_hi term] = three tiles.
+                const char* en = getenv("UMX_TC_NCAT");
+                const char* em = getenv("UMX_TC_MERGE_PX");
+                const bool will_merge = sp.transpose && tp.nphase == 4 && 2 * tp.n_t <= 256 && !narrow && op.fuse_top < 0 && (em ? atoi(em) : 1);
+                const size_t res3 = ((size_t)nc0 * ntaps_w * 3 + (size_t)nc1 * (tp.a1_center ? tp.res_c_planes : ntaps_w * 3)) * tile;
+                // (measured, Cyto2: lu0.conv2+lt, N = 32, 120 -> 96 ms; the conv-transposes - few MMAs per accumulator, epilogue-bound -
+                // lose 20 % to the second TMEM read, and from N = 64 on the wide MMA costs what two narrow ones do: not used there.
+                // The path is compiled into the kernels with the fused lt epilogue only: in the others the extra epilogue code
+                // alone cost the conv-transposes 7 %)
+                const bool ncat_pays = op.fuse_top >= 0 && !sp.transpose && tp.n_t <= 48;
+                if ((e ? atoi(e) : 1) && (en ? atoi(en) != 0 && ncat_pays : ncat_pays) && tp.pair && tp.planes_b == 2 &&
+                    ((tp.terms0 | tp.terms1) & 1) && tp.n_ntiles == 1 &&
+                    ntaps_w <= 9 && 2 * tp.n_t * (will_merge ? 2 : 1) <= 256 && budget >= res3 + (tp.planes_a == 2 ? 2 : 3) * ab) {
+                    tp.ncat = 1; tp.res_m_planes = 3;
+                    tp.b_resident = 1; tp.gb = ntaps_w; tp.b_stages = n_chunks; tp.b_res_bytes = (int32_t)res3;
+                    tp.stages = (int)std::min<size_t>(6, (budget - res3) / ab);
+                }
                 // (with both activation planes in a patch slot two slots are accepted - in this mode nothing but patches
                 // moves, so no patch waits behind a weight load)
-                if ((e ? atoi(e) : 1) && tp.n_ntiles == 1 && ntaps_w <= 9 && tp.res_m_planes <= tp.planes_b && budget >= res + (tp.planes_a == 2 ? 2 : 3) * ab) {
+                else if ((e ? atoi(e) : 1) && tp.n_ntiles == 1 && ntaps_w <= 9 && tp.res_m_planes <= tp.planes_b && budget >= res + (tp.planes_a == 2 ? 2 : 3) * ab) {
                     tp.b_resident = 1; tp.gb = ntaps_w; tp.b_stages = n_chunks; tp.b_res_bytes = (int32_t)res;
                     tp.stages = (int)std::min<size_t>(6, (budget - res) / ab);
                 }
@@ -703,7 +724,7 @@ int lower_conv_tc(umx_handle* h, Op& op) {
     UMX_CUDA_TRY(cudaMalloc(&dw, wh.size() * sizeof(__half)));
     h->dev_allocs.push_back(reinterpret_cast<float*>(dw));
     UMX_CUDA_TRY(cudaMemcpy(dw, wh.data(), wh.size() * sizeof(__half), cudaMemcpyHostToDevice));
-    int rc = make_weight_tensor_map(&op.mapB, dw, planes_b, taps_dev, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, tp.b_resident ? tp.res_m_planes : planes_b, box_taps);
+    int rc = make_weight_tensor_map(&op.mapB, dw, planes_b, taps_dev, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, tp.ncat ? 1 : (tp.b_resident ? tp.res_m_planes : planes_b), tp.ncat ? 1 : box_taps);     // ncat: one-tile boxes (plane, tap, half of the rows)
     if (rc) { set_error("%s: cuTensorMapEncodeTiled(weights) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
     op.mapB1 = op.mapB;
     if (tp.halo && !tp.b_resident && planes_b == 2 && (!(tp.terms0 & 1) || (a1 && !(tp.terms1 & 1)))) {
@@ -712,7 +733,7 @@ int lower_conv_tc(umx_handle* h, Op& op) {
         if (rc) { set_error("%s: cuTensorMapEncodeTiled(weights, hi plane) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
         tp.b1_hi_only = 1;
     }
-    if (tp.b_resident && tp.a1_center) {
+    if (tp.b_resident && tp.a1_center && !tp.ncat) {
         rc = make_weight_tensor_map(&op.mapB1, dw, planes_b, taps_dev, sp.cout, cin, tp.pair ? tp.n_t / 2 : tp.n_t, tp.res_c_planes, 1);
         if (rc) { set_error("%s: cuTensorMapEncodeTiled(weights, one tap) failed (%d)", op.name.c_str(), rc); return UMX_ECUDA; }
     }
@@ -1163,7 +1184,7 @@ int umx_op_info(umx_handle* h, int32_t op_index, int32_t* out, int32_t capacity)
     const TcConvParams& tp = op.tcp;
     const bool tc = op.kind == OP_CONV && op.use_tc;
     const int v[12] = {tc ? 1 : 0, tc ? tp.halo : 0, tc ? tp.pair : 0, tc ? tp.stages : 0, tc ? tp.b_stages : 0, tc ? tp.gb : 0,
-                       tc ? tp.b_resident : 0, tc ? tp.merge_px : 0, tc ? tp.planes_a : 0, tc ? tp.planes_b : 0,
+                       tc ? (tp.ncat ? 2 : tp.b_resident) : 0, tc ? tp.merge_px : 0, tc ? tp.planes_a : 0, tc ? tp.planes_b : 0,
                        tc ? tp.terms0 : 0, tc ? tp.terms1 : 0};
     for (int i = 0; i < 12; ++i) out[i] = v[i];
     return UMX_OK;

@@ -38,7 +38,8 @@ struct TcConvParams {
     int32_t b_res_bytes;         // bytes of the resident weight region (per CTA)
     int32_t b1_hi_only;          // streamed (non-resident) halo mode with hi + lo weights: mapB1 is the same box with the hi plane only,
                                  // used for the slabs of a source that has no a_hi*w_lo term
-    int32_t res_m_planes;        // resident mode: weight planes of a full slab (all taps): 1 = hi, 2 = hi + lo
+    int32_t ncat;                // resident mode, CTA pairs: a_hi x [w_hi | w_lo] as one MMA of width 2*n_t, halves added in the epilogue
+    int32_t res_m_planes;        // resident mode: weight tiles per tap of a full slab: 1 = hi, 2 = hi + lo ([plane][tap]), 3 = ncat ([tap][X, X, Y])
     int32_t res_c_planes;        // resident mode: weight planes a centre-only (1x1 term) slab keeps: 1 = hi, 2 = hi + lo (its a_hi*w_lo term is on)
     int32_t b_resident;          // halo mode: every (slab, tap) weight tile of the layer stays in shared memory (one slot of gb = all taps per slab)
     int32_t kslab;               // plain mode: 64-channel slabs per ring slot (more MMAs per barrier round trip)

@@ -408,6 +408,8 @@ def calibrate(model: Model, device: int = 0, probe_tiles: Optional[np.ndarray] =
             report["chosen"] = "single"
             return "single", {}, report
         prof_split = profile_of(ref)
+        # layers that multiply a_hi by [w_hi | w_lo] in one wide MMA (umx_op_info: resident == 2): the a_hi*w_lo term is free there
+        ncat_ops = {i for i, _, _ in srcs if ref.op_info(i)["resident"] == 2}
         # per op: (terms, error alone, time by the linear model, time if hi-only weights stay resident)
         measured: Dict[int, List[Tuple[int, float, float, float]]] = {}
         layers = []
@@ -429,6 +431,9 @@ def calibrate(model: Model, device: int = 0, probe_tiles: Optional[np.ndarray] =
                     # (the one-tile slab of a 1x1 term - a tap-expanded raw input, K < 64 - may keep its lo plane too)
                     hi_only = not (t0 & 1) and (not two or not (t1 & 1) or k1 < 64)
                     t_res = t_single * (1.0 + 1.55 * share) if (i in resident and hi_only) else t_single + (t_split - t_single) * min(1.0, 1.2 * share)
+                    if i in ncat_ops:
+                        share_n = (k0 * ((t0 >> 1) & 1) + k1 * ((t1 >> 1) & 1)) / (k0 + k1)
+                        t_lin = t_res = t_single + (t_split - t_single) * share_n
                     if terms == 15 or (not two and t0 == 3):
                         err = 0.0
                     else:
