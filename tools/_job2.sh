@@ -1,8 +1,5 @@
-timeout 300 python -m pytest tests -m gpu -x -q -k "multi" 2>&1 | tail -3
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --size 8192 --steps 3 --warmup 2 --cpu-budget 0 --configs none --no-modes > /tmp/b2.json 2>/tmp/b2.err
-tail -c 300 /tmp/b2.err
-python - <<'PY'
-import json
-d=json.loads(open("/tmp/b2.json").read().strip().splitlines()[-1])
-print(d["value"], d["n_gpus"], d["bands_bit_exact"], d["per_rank"], d["stitched_u8"])
-PY
+mkdir -p gpurun_out/r2/final3
+timeout 300 ncu --set full --clock-control none --import-source on --nvtx --nvtx-include "timed_resident/" -k regex:"first_conv|stitch" -c 2 -o /tmp/simt python bench.py --size 4096 --steps 1 --warmup 1 --cpu-budget 0 --configs none --no-modes --no-crop-check > gpurun_out/r2/final3/ncu.log 2>&1
+ncu -i /tmp/simt.ncu-rep --page raw --csv > gpurun_out/r2/final3/simt_raw.csv 2>/dev/null
+python tools/ncu_summary.py gpurun_out/r2/final3/simt_raw.csv gpurun_out/r2/final3/r2_ncu_full_simt_4k.json "ncu --set full --clock-control none --nvtx --nvtx-include timed_resident/ -k regex:first_conv|stitch -c 2 python bench.py --size 4096 --steps 1 --warmup 1 (final build)" "ld0.conv0+gather+taps,stitch_quantize"
+tail -3 gpurun_out/r2/final3/ncu.log
